@@ -1,0 +1,249 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference (/root/reference).
+
+Runs only in the build container (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+The reference is imported through tests/golden/refshim.py (stand-ins for the absent ultralytics / matplotlib
+packages).  All inputs are regenerated from seeds by oracle/* helpers (numpy RandomState: portable), so the
+fixtures only hold the reference's OUTPUTS.  While generating, every oracle function is checked against the
+reference output (hard assert) -- this is what pins the oracle.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import refshim  # noqa: E402
+
+refshim.install()
+
+import torch  # noqa: E402
+import torchvision  # noqa: E402
+import yaml  # noqa: E402
+
+from oracle import loss_ref, model_ref, nms_ref  # noqa: E402
+from yolov5_b200.cfg import HYP_SCRATCH_LOW, model_cfg, model_names  # noqa: E402
+
+torch.set_num_threads(8)
+REF = refshim.REFERENCE_ROOT
+
+
+def synth_image(shape, seed):
+    return torch.from_numpy(np.random.RandomState(seed).uniform(0, 1, shape).astype(np.float32))
+
+
+def cfg_digest(cfg):
+    return hashlib.sha256(json.dumps(cfg, sort_keys=True).encode()).hexdigest()
+
+
+def gen_cfg():
+    out = {}
+    for name in model_names():
+        sub = "models/segment/" if name.endswith("-seg") else "models/"
+        with open(f"{REF}/{sub}{name}.yaml", encoding="ascii", errors="ignore") as f:
+            ref = yaml.safe_load(f)
+        assert ref == model_cfg(name), name
+        out[name] = cfg_digest(ref)
+    with open(f"{REF}/data/hyps/hyp.scratch-low.yaml") as f:
+        hyp = yaml.safe_load(f)
+    for k, v in HYP_SCRATCH_LOW.items():
+        if k != "label_smoothing":
+            assert hyp[k] == v, k
+    json.dump(out, open(f"{HERE}/cfg_digest.json", "w"), indent=1)
+    print("cfg tables == reference YAML for", list(out))
+
+
+def ref_model(name, sd):
+    from models.yolo import DetectionModel, SegmentationModel
+
+    sub = "models/segment/" if name.endswith("-seg") else "models/"
+    cls = SegmentationModel if name.endswith("-seg") else DetectionModel
+    m = cls(f"{REF}/{sub}{name}.yaml")
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    # the reference divides its anchors by the probed stride at construction; our synthetic sd already holds them
+    return m.eval()
+
+
+def gen_model():
+    cases = [("yolov5n", (2, 3, 96, 128), 10), ("yolov5s", (1, 3, 64, 64), 11), ("yolov5n-seg", (1, 3, 64, 96), 12)]
+    store = {}
+    for name, shape, seed in cases:
+        cfg = model_cfg(name)
+        sd = model_ref.synth_state_dict(cfg, seed=seed)
+        m = ref_model(name, sd)
+        assert [float(s) for s in m.stride] == model_ref.model_strides(cfg)
+        x = synth_image(shape, seed + 100)
+        with torch.no_grad():
+            y_ref = m(x)
+            y_orc = model_ref.forward(cfg, sd, x)
+            mf = ref_model(name, sd).fuse()
+            yf_ref = mf(x)
+            yf_orc = model_ref.forward(cfg, sd, x, fused=True)
+            m.train()
+            yt_ref = m(x)  # NB train mode also updates BN running stats; outputs use batch stats -> not compared
+            yt_orc = None
+        seg = name.endswith("-seg")
+        for tag, r, o in (("bn", y_ref, y_orc), ("fused", yf_ref, yf_orc)):
+            z_r, z_o = r[0], o[0]
+            raw_r, raw_o = (r[2], o[2]) if seg else (r[1], o[1])
+            d = (z_r - z_o).abs().max().item()
+            print(f"{name} {tag}: z max|ref-oracle| = {d:.3e}  (|z|max {z_r.abs().max():.1f})")
+            assert torch.allclose(z_r, z_o, rtol=1e-4, atol=1e-4), (name, tag, d)
+            for a, b in zip(raw_r, raw_o):
+                assert torch.allclose(a, b, rtol=1e-4, atol=1e-4)
+            store[f"{name}.{tag}.z"] = z_r.numpy()
+            for l, a in enumerate(raw_r):
+                store[f"{name}.{tag}.raw{l}"] = a.numpy()
+            if seg:
+                assert torch.allclose(r[1], o[1], rtol=1e-4, atol=1e-4)
+                store[f"{name}.{tag}.proto"] = r[1].numpy()
+        store[f"{name}.shape"] = np.array(shape)
+        store[f"{name}.seed"] = np.array([seed, seed + 100])
+    # config 1 of BASELINE.json: yolov5n, 1x3x640x640, CPU fp32 -- keep a strided sample + checksum only
+    cfg = model_cfg("yolov5n")
+    sd = model_ref.synth_state_dict(cfg, seed=20, head_bias="hot")
+    m = ref_model("yolov5n", sd).fuse()
+    x = synth_image((1, 3, 640, 640), 120)
+    with torch.no_grad():
+        z = m(x)[0]
+        zo = model_ref.forward(cfg, sd, x, fused=True)[0]
+    assert z.shape == (1, 25200, 85)
+    assert torch.allclose(z, zo, rtol=1e-4, atol=1e-4), (z - zo).abs().max()
+    store["yolov5n.640.z_sample"] = z[0, ::97].numpy()
+    store["yolov5n.640.z_sum"] = np.array([z.double().sum().item(), z.double().abs().sum().item()])
+    store["yolov5n.640.seed"] = np.array([20, 120])
+    print("yolov5n 640 max|ref-oracle| =", (z - zo).abs().max().item(), " obj>0.25 rows:", int((z[0, :, 4] > 0.25).sum()))
+    np.savez_compressed(f"{HERE}/model_forward.npz", **store)
+
+
+def run_ref_nms(pred_np, dtype, **kw):
+    from utils.general import non_max_suppression
+
+    tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[dtype]
+    outs = []
+    for b in range(pred_np.shape[0]):  # one image per call so the reference's wall-clock abort cannot drop images
+        out = non_max_suppression(torch.from_numpy(pred_np[b : b + 1]).to(tdt), **kw)
+        assert out[0].dtype == torch.float32
+        outs.append(out[0].numpy())
+    return outs
+
+
+def canon_ties(d):
+    """Sort rows by (-score, then all columns) so rows with equal score are in a canonical order."""
+    keys = [d[:, k] for k in range(d.shape[1] - 1, -1, -1) if k != 4] + [-d[:, 4]]
+    return d[np.lexsort(keys)]
+
+
+def gen_nms():
+    rs = np.random.RandomState(7)
+    # (1) the greedy core vs the installed torchvision op, including ties / zero-area / identical boxes
+    for trial in range(40):
+        n = int(rs.randint(1, 400))
+        xy = rs.uniform(0, 100, (n, 2)).astype(np.float32)
+        wh = rs.uniform(0, 40, (n, 2)).astype(np.float32)
+        if trial % 4 == 0:
+            xy, wh = np.round(xy / 8) * 8, np.round(wh / 8) * 8  # many exact ties and zero areas
+        boxes = np.concatenate((xy, xy + wh), 1).astype(np.float32)
+        scores = np.sort(rs.uniform(0, 1, n).astype(np.float32))[::-1].copy()
+        thr = float(rs.choice([0.3, 0.45, 0.6]))
+        ref = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+        got = nms_ref.nms_greedy(boxes, thr)
+        assert np.array_equal(ref, got), trial
+    print("nms_greedy == torchvision.ops.nms on 40 random cases")
+    # box_iou vs the shim's torch expression
+    a = np.concatenate((xy[:50], xy[:50] + wh[:50]), 1)
+    b = np.concatenate((xy[50:90], xy[50:90] + wh[50:90]), 1) if n > 90 else a
+    ref_iou = refshim.box_iou(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+    assert np.allclose(ref_iou, nms_ref.box_iou(a, b), rtol=1e-6, atol=1e-7)
+
+    # (2) whole function vs the reference, several regimes
+    store, meta = {}, []
+    cases = [
+        dict(tag="detect_fp32", bs=3, n=25200, nc=80, nm=0, seed=2, dtype="fp32", kw=dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)),
+        dict(tag="detect_fp16", bs=3, n=25200, nc=80, nm=0, seed=3, dtype="fp16", kw=dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)),
+        dict(tag="detect_bf16", bs=2, n=25200, nc=80, nm=0, seed=4, dtype="bf16", kw=dict(conf_thres=0.25, iou_thres=0.45, max_det=1000)),
+        dict(tag="val_fp32", bs=2, n=25200, nc=80, nm=0, seed=5, dtype="fp32", kw=dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)),
+        dict(tag="val_fp16", bs=2, n=25200, nc=80, nm=0, seed=6, dtype="fp16", kw=dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300)),
+        dict(tag="agnostic_cls", bs=2, n=6300, nc=80, nm=0, seed=7, dtype="fp16", kw=dict(conf_thres=0.25, iou_thres=0.45, agnostic=True, classes=[0, 3, 17, 40, 79], max_det=300)),
+        dict(tag="seg_fp16", bs=2, n=6300, nc=80, nm=32, seed=8, dtype="fp16", kw=dict(conf_thres=0.25, iou_thres=0.45, max_det=300, nm=32)),
+        dict(tag="small_nc1", bs=2, n=1000, nc=1, nm=0, seed=9, dtype="fp32", kw=dict(conf_thres=0.1, iou_thres=0.5, multi_label=True, max_det=50)),
+        dict(tag="empty", bs=2, n=500, nc=80, nm=0, seed=10, dtype="fp16", kw=dict(conf_thres=0.9999, iou_thres=0.45)),
+    ]
+    for c in cases:
+        pred = nms_ref.synth_predictions(c["bs"], c["n"], c["nc"], c["nm"], c["seed"], c["dtype"])
+        ref = run_ref_nms(pred, c["dtype"], **c["kw"])
+        orc = nms_ref.non_max_suppression(pred, dtype=c["dtype"], **c["kw"])
+        how = "bit-exact"
+        for b, (r, o) in enumerate(zip(ref, orc)):
+            assert r.shape == o.shape, (c["tag"], b, r.shape, o.shape)
+            if not np.array_equal(r, o):
+                # equal scores: the reference's argsort(descending=True) (utils/general.py:745) is not a stable sort,
+                # so the order inside an equal-score run is implementation-defined there; the oracle (and the CUDA
+                # path) define it as candidate order.  Compare with each equal-score run put in a canonical order.
+                assert np.array_equal(canon_ties(r), canon_ties(o)), (c["tag"], b)
+                how = "exact up to the order inside equal-score runs"
+            store[f"{c['tag']}.{b}"] = o
+        c["pinned"] = how
+        meta.append({k: v for k, v in c.items()})
+        print(f"NMS {c['tag']}: oracle == reference {how}; dets/img {[r.shape[0] for r in ref]}")
+    store["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(f"{HERE}/nms.npz", **store)
+
+
+def gen_loss():
+    from models.yolo import DetectionModel
+    from utils.loss import ComputeLoss
+
+    cfg = model_cfg("yolov5n")
+    sd = model_ref.synth_state_dict(cfg, seed=30)
+    m = DetectionModel(f"{REF}/models/yolov5n.yaml")
+    m.load_state_dict(sd)
+    m.hyp = dict(HYP_SCRATCH_LOW)
+    crit = ComputeLoss(m)
+    anchors = sd["model.24.anchors"].numpy()
+    store = {}
+    for tag, bs, hw, seed in (("a", 4, (128, 160), 31), ("b", 16, (64, 64), 32), ("none", 2, (64, 64), 33)):
+        rs = np.random.RandomState(seed)
+        p = [torch.from_numpy(rs.normal(0, 1.5, (bs, 3, hw[0] // s, hw[1] // s, 85)).astype(np.float32)).requires_grad_(True) for s in (8, 16, 32)]
+        tg = loss_ref.synth_targets(bs, seed) if tag != "none" else np.zeros((0, 6), np.float32)
+        loss, items = crit(p, torch.from_numpy(tg))
+        loss.backward()
+        tcls, tbox, indices, anch = crit.build_targets(p, torch.from_numpy(tg))
+        bt = loss_ref.build_targets(tg, anchors, [tuple(pi.shape[2:4]) for pi in p], 4.0)
+        for i in range(3):
+            assert np.array_equal(tcls[i].numpy(), bt[i]["tcls"])
+            assert np.array_equal(tbox[i].numpy(), bt[i]["tbox"]), np.abs(tbox[i].numpy() - bt[i]["tbox"]).max()
+            for q, k in enumerate(("b", "a", "gj", "gi")):
+                assert np.array_equal(indices[i][q].numpy(), bt[i][k]), (tag, i, k)
+            assert np.array_equal(anch[i].numpy(), bt[i]["anch"])
+            store[f"{tag}.idx{i}"] = np.stack([indices[i][q].numpy() for q in range(4)] + [tcls[i].numpy()])
+            store[f"{tag}.tbox{i}"] = tbox[i].numpy()
+        p2 = [t.detach().clone().requires_grad_(True) for t in p]
+        lo, it = loss_ref.compute_loss(p2, tg, anchors, HYP_SCRATCH_LOW)
+        lo.backward()
+        assert torch.allclose(loss, lo, rtol=1e-5, atol=1e-6), (loss, lo)
+        assert torch.allclose(items, it, rtol=1e-5, atol=1e-6)
+        for a, b in zip(p, p2):
+            assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-7), (a.grad - b.grad).abs().max()
+        store[f"{tag}.loss"] = np.concatenate((loss.detach().numpy(), items.numpy()))
+        store[f"{tag}.gradsum"] = np.array([[t.grad.double().sum().item(), t.grad.double().abs().sum().item()] for t in p])
+        store[f"{tag}.grad_sample0"] = p[0].grad.numpy().reshape(-1)[::1009]
+        store[f"{tag}.meta"] = np.array([bs, hw[0], hw[1], seed])
+        print(f"loss {tag}: {loss.item():.6f} items {items.tolist()} matches {[len(d['b']) for d in bt]}; oracle == reference")
+    np.savez_compressed(f"{HERE}/loss.npz", **store)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg", "model", "nms", "loss"]
+    for w in which:
+        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss}[w]()
+    print("golden fixtures written to", HERE)
