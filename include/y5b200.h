@@ -1,0 +1,196 @@
+/* y5b200.h -- C ABI of liby5b200.so: the B200 (sm_100a) engine behind the YOLOv5 forward / NMS / loss hot path.
+ *
+ * The reference (ultralytics/yolov5) is pure Python and has NO FFI / plugin interface for this path: the work
+ * sits behind ordinary Python callables.  Each entry point below therefore names the
+ * reference callable whose body it replaces (file:line under /root/reference); INTEGRATION.md shows the ctypes
+ * stubs a maintainer adds to those files.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; device pointers are raw CUDA device addresses; `stream` is a cudaStream_t;
+ *   - never allocate device memory, never synchronise the stream, never touch the default stream;
+ *   - activations are NHWC ("pixel-major"): element (n,y,x,c) of a view lives at base[((n*H+y)*W+x)*pitch + c],
+ *     where `pitch` (elements per pixel of the underlying buffer) >= the view's channel count -- a view may be a
+ *     channel slice of a wider buffer (this is how torch.cat is eliminated); pitches and channel offsets are
+ *     multiples of 8 elements (16 bytes);
+ *   - dtype: Y5_F16 or Y5_BF16 for activations and packed weights; accumulation and bias are fp32;
+ *   - return 0 on success, a negative Y5_E* code for a rejected argument, a positive cudaError_t for a CUDA
+ *     failure; y5_last_error() returns a thread-local message for the last non-zero return.
+ */
+#ifndef Y5B200_H
+#define Y5B200_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define Y5_API __attribute__((visibility("default")))
+#else
+#define Y5_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y5_F16 0
+#define Y5_BF16 1
+#define Y5_F32 2
+#define Y5_U8 3
+
+#define Y5_E_INVALID (-1)     /* bad argument (null pointer, misaligned pitch, ...) */
+#define Y5_E_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define Y5_E_DRIVER (-3)      /* tensor-map encode / driver entry point unavailable */
+
+#define Y5_ACT_NONE 0
+#define Y5_ACT_SILU 1
+
+int y5_version(void);
+const char* y5_last_error(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t y5_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused Conv2d(bias=False) + folded BatchNorm + SiLU (+ residual add), implicit GEMM on tcgen05 tensor cores.
+ * Replaces: models/common.py:86-92 Conv.forward / forward_fuse (conv -> bn -> act), utils/torch_utils.py:224-254
+ * (BN fold, done once by the caller when packing), models/common.py:181 Bottleneck's `x + ...` (residual),
+ * and, through out pitch/offset, the torch.cat of models/common.py:246,340,453.
+ *   weights : packed [out_c][kh][kw][cin_pad] (K-major), cin_pad = chunks*block_k as reported by y5_conv_pick,
+ *             zero padded, dtype = activation dtype, BN scale already folded in
+ *   bias    : fp32 [out_c] (folded BN shift)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct y5_conv_desc {
+    const void* in;       /* view base (already offset to its first channel) */
+    int32_t in_pitch;     /* elements per pixel of the buffer holding the view */
+    int32_t batch, in_h, in_w, in_c;
+    const void* weight;
+    const float* bias;
+    void* out;            /* view base (already offset to its first channel) */
+    int32_t out_pitch;
+    int32_t out_c;
+    const void* residual; /* optional: same shape as out; may alias out (in-place add) */
+    int32_t res_pitch;
+    int32_t ksize, stride, pad;
+    int32_t act;          /* Y5_ACT_* */
+    int32_t dtype;        /* Y5_F16 | Y5_BF16 */
+    int32_t block_k;      /* 16|32|64, or 0 = y5_conv_pick's choice; must match the weight packing */
+    int32_t block_n;      /* 32|64|128|256, or 0 = auto */
+} y5_conv_desc;
+
+/* Tiling the library will use for a conv: block_k decides the weight packing (cin_pad = ceil(in_c/block_k)*block_k). */
+int y5_conv_pick(int32_t in_c, int32_t out_c, int64_t m_rows, int32_t* block_k, int32_t* block_n);
+
+typedef struct y5_conv_plan y5_conv_plan; /* opaque: encoded TMA descriptors + launch geometry for fixed pointers */
+int y5_conv_plan_create(const y5_conv_desc* desc, y5_conv_plan** plan);
+int y5_conv_plan_run(const y5_conv_plan* plan, void* stream);
+void y5_conv_plan_destroy(y5_conv_plan* plan);
+/* one-shot convenience: create + run + destroy (tests) */
+int y5_conv_bn_silu_fwd(const y5_conv_desc* desc, void* stream);
+/* independent direct-convolution kernel (CUDA cores, fp32 accumulate) used by tests to cross-check the tensor-core
+ * path on the device; same descriptor, weights in the same packed layout */
+int y5_conv_direct_fwd(const y5_conv_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Detect / Segment head level: 1x1 conv with bias + reshape + sigmoid/grid/anchor decode in the GEMM epilogue.
+ * Replaces models/yolo.py:95-113 for one level i (conv, view/permute, sigmoid, xy/wh decode, cat into z).
+ *   raw : (B, na, ny, nx, no)  un-activated logits, activation dtype            (x[i] of the reference)
+ *   z   : (B, z_rows, no) decoded rows; this level writes rows [z_row0, z_row0 + na*ny*nx) of every image
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct y5_detect_desc {
+    const void* in;
+    int32_t in_pitch;
+    int32_t batch, ny, nx, in_c;
+    const void* weight;   /* packed [na*no][cin_pad] */
+    const float* bias;    /* fp32 [na*no] */
+    void* raw;
+    void* z;
+    int32_t z_rows, z_row0;
+    int32_t na, no, nc;   /* no = 5 + nc + nm; columns >= 5+nc (mask coefficients) are passed through un-sigmoided */
+    float stride;         /* pixels per cell of this level */
+    float anchor_wh[8];   /* na x (w,h) in PIXELS (= anchors * stride), na <= 4 */
+    int32_t dtype;
+    int32_t block_k;
+} y5_detect_desc;
+typedef struct y5_detect_plan y5_detect_plan;
+int y5_detect_plan_create(const y5_detect_desc* desc, y5_detect_plan** plan);
+int y5_detect_plan_run(const y5_detect_plan* plan, void* stream);
+/* same plan, outputs redirected to freshly allocated tensors of the same shapes (the reference returns new tensors
+ * from every forward; the input side of the plan stays bound to the engine's static buffers) */
+int y5_detect_plan_run_to(const y5_detect_plan* plan, void* raw, void* z, void* stream);
+void y5_detect_plan_destroy(y5_detect_plan* plan);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Data-movement kernels (HBM bound)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Stem input: NCHW image (Y5_U8 scaled by 1/255, or Y5_F16/Y5_BF16/Y5_F32 already in [0,1]) -> 2x2 space-to-depth
+ * NHWC with 16 channels (12 used: (dy*2+dx)*3 + c; 4 zero), so that the 6x6/s2/p2 stem conv of
+ * models/yolov5s.yaml:20 becomes a 3x3/s1/p1 conv over 16 channels.  Replaces the `im.half(); im /= 255` of
+ * detect.py:206-208 / val.py:259-262 plus the layout change.  h, w even. */
+int y5_stem_s2d(const void* img, int32_t img_dtype, void* out, int32_t out_dtype, int32_t batch, int32_t h, int32_t w,
+                void* stream);
+/* SPPF pooling (models/common.py:338-340): reads view x (c channels), writes maxpool5, maxpool5^2 (=9x9),
+ * maxpool5^3 (=13x13) into three views (usually channel slices 1..3 of the buffer whose slice 0 is x). */
+int y5_sppf_pool(const void* x, int32_t x_pitch, void* y1, void* y2, void* y3, int32_t y_pitch, int32_t batch, int32_t h,
+                 int32_t w, int32_t c, int32_t ksize, int32_t dtype, void* stream);
+/* nn.Upsample(scale_factor=2, mode='nearest') written straight into a (concat) view. */
+int y5_upsample2x(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int32_t batch, int32_t h, int32_t w, int32_t c,
+                  int32_t dtype, void* stream);
+/* strided channel-slice copy (only needed when a tensor feeds two concat buffers) */
+int y5_copy_view(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int64_t pixels, int32_t c, int32_t dtype,
+                 void* stream);
+/* NHWC view -> dense NCHW tensor (the API hands NCHW tensors back to PyTorch callers, e.g. Segment's proto) */
+int y5_nhwc_to_nchw(const void* x, int32_t x_pitch, void* y, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * non_max_suppression (utils/general.py:658-767) for a whole batch in one launch set; bit-exact indices.
+ *   pred     : (B, N, no) decoded predictions, dtype Y5_F16 | Y5_BF16 | Y5_F32, dense
+ *   classes  : optional device array of class ids to keep (int32), n_classes entries
+ *   out_rows : (B, max_det, 6+nm) fp32   [x1,y1,x2,y2,conf,cls,masks...]
+ *   out_idx  : (B, max_det) int64        candidate id = row*nc + cls of each kept detection
+ *   out_count: (B) int32                 detections kept per image
+ *   workspace: y5_nms_workspace_bytes(...) bytes of scratch
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct y5_nms_params {
+    int32_t batch, n_rows, no, nc, nm;
+    int32_t dtype;
+    float conf_thres, iou_thres;
+    int32_t multi_label, agnostic;
+    int32_t max_det;  /* reference default 300 */
+    int32_t max_nms;  /* reference constant 30000 */
+    float max_wh;     /* reference constant 7680 */
+    const int32_t* classes;
+    int32_t n_classes;
+} y5_nms_params;
+int64_t y5_nms_workspace_bytes(const y5_nms_params* p);
+int y5_nms_batched(const y5_nms_params* p, const void* pred, float* out_rows, int64_t* out_idx, int32_t* out_count,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* box_iou (ultralytics.utils.metrics.box_iou as used by utils/metrics.py:158,252): (n,4) x (m,4) -> (n,m), fp32 */
+int y5_box_iou(const float* a, int32_t n, const float* b, int32_t m, float eps, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ComputeLoss (utils/loss.py:134-247): build_targets + gather/CIoU/scatter + BCE, forward and backward.
+ *   p[l]      : (B, na, ny_l, nx_l, no) logits, dtype Y5_F16 | Y5_BF16 | Y5_F32
+ *   targets   : (nt, 6) fp32 [img, cls, x, y, w, h]
+ *   anchors   : (nl, na, 2) fp32, grid units
+ *   out_loss  : fp32[4] = [loss*bs, lbox, lobj, lcls]  (gains already applied)
+ *   grad[l]   : optional, same shape AND dtype as p[l]: d(out_loss[0] * grad_scale)/dp  (fully written)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct y5_loss_params {
+    int32_t nl, batch, na, no, nc;
+    int32_t ny[5], nx[5];
+    int32_t dtype;
+    int32_t nt;
+    float anchor_t, box_gain, obj_gain, cls_gain, cls_pw, obj_pw, cp, cn;
+    float balance[5];
+    float grad_scale;
+} y5_loss_params;
+int64_t y5_loss_workspace_bytes(const y5_loss_params* p);
+/* matches: per level, int32 count + rows (b, a, gj, gi, cls) int64 and tbox fp32 live in the workspace; the
+ * build_targets result can be read back with y5_loss_read_targets for parity tests */
+int y5_loss_fwd_bwd(const y5_loss_params* p, const void* const* pl, const float* targets, const float* anchors,
+                    float* out_loss, void* const* grad, void* workspace, int64_t workspace_bytes, void* stream);
+int y5_loss_read_targets(const y5_loss_params* p, const void* workspace, int32_t level, int64_t* idx5_host,
+                         float* tbox_host, int32_t* count_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Y5B200_H */

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/y5b200.h declares
+(no compute calls here -- there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from yolov5_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "y5b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(y5_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    names = _declared()
+    for must in ("y5_conv_plan_create", "y5_conv_plan_run", "y5_detect_plan_create", "y5_stem_s2d", "y5_sppf_pool",
+                 "y5_upsample2x", "y5_nms_batched", "y5_box_iou", "y5_loss_fwd_bwd", "y5_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in _declared() if not hasattr(handle, n)]
+    assert not missing, missing
+    assert sorted(_lib.SIGNATURES) == _declared()  # the ctypes table mirrors the header one to one
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(built_lib):
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.4D.IM2COL"):  # tcgen05.mma, TMA, tcgen05.ld, im2col TMA
+        assert mnemonic in sass, mnemonic
+
+
+def test_argument_validation_without_gpu(built_lib):
+    lib = built_lib
+    assert lib.y5_version() == 1
+    d = _lib.ConvDesc()  # all null
+    plan = ctypes.c_void_p()
+    assert lib.y5_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)) == -1  # Y5_E_INVALID
+    assert b"null" in lib.y5_last_error()
+    p = _lib.NmsParams()
+    p.batch, p.n_rows, p.no, p.nc, p.nm, p.dtype = 2, 100, 85, 80, 0, _lib.Y5_F16
+    p.conf_thres, p.iou_thres, p.max_det, p.max_nms = 0.25, 0.45, 300, 30000
+    assert lib.y5_nms_workspace_bytes(ctypes.byref(p)) > 0
+    p.no = 84
+    assert lib.y5_nms_workspace_bytes(ctypes.byref(p)) == -1
+    bk, bn = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.y5_conv_pick(128, 256, 51200, ctypes.byref(bk), ctypes.byref(bn)) == 0
+    assert bk.value == 64 and bn.value in (128, 256)

@@ -1,0 +1,97 @@
+"""CPU: host-side logic of the engine -- model assembly parity with the reference's structure, weight folding /
+packing, the stem space-to-depth identity, and the loud failure on non-CUDA inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model_ref
+from yolov5_b200.cfg import model_cfg
+from yolov5_b200.engine import fold_conv_bn, pack_weight, stem_weight_s2d
+from yolov5_b200.models.common import C3, Conv
+from yolov5_b200.models.yolo import DetectionModel, SegmentationModel
+from yolov5_b200.utils.general import _iou_threshold_f32
+from yolov5_b200.utils.torch_utils import fuse_conv_and_bn
+
+PARAMS = {"yolov5n": 1872157, "yolov5s": 7235389, "yolov5m": 21190557, "yolov5l": 46563709, "yolov5x": 86749405,
+          "yolov5x-seg": 88819517}  # SURVEY.md Appendix A (counted on the reference)
+
+
+@pytest.mark.parametrize("name", list(PARAMS))
+def test_parameter_counts_and_state_dict_keys(name):
+    m = (SegmentationModel if name.endswith("-seg") else DetectionModel)(name)
+    assert sum(p.numel() for p in m.parameters()) == PARAMS[name]
+    assert list(m.state_dict().keys()) == list(model_ref.param_shapes(model_cfg(name)).keys())
+    assert [float(s) for s in m.stride] == [8.0, 16.0, 32.0]
+    assert m.save == [4, 6, 10, 14, 17, 20, 23]
+    assert m.model[0].bn.eps == 1e-3 and m.model[0].bn.momentum == 0.03
+
+
+def test_stem_space_to_depth_identity():
+    """6x6/s2/p2 conv on 3 channels == 3x3/s1/p1 conv on the 2x2 space-to-depth tensor (12 of 16 channels used)."""
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 32, 48)
+    w = torch.randn(8, 3, 6, 6)
+    ref = F.conv2d(x, w, stride=2, padding=2)
+    b, _, h, wd = x.shape
+    s2d = torch.zeros(b, 16, h // 2, wd // 2)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                s2d[:, (dy * 2 + dx) * 3 + c] = x[:, c, dy::2, dx::2]
+    got = F.conv2d(s2d, stem_weight_s2d(w), stride=1, padding=1)
+    assert torch.allclose(ref, got, atol=1e-4)
+
+
+def test_fold_matches_oracle_and_fuse():
+    torch.manual_seed(1)
+    m = Conv(16, 24, 3, 1)
+    m.bn.weight.data.uniform_(0.5, 1.5); m.bn.bias.data.normal_(0, 0.1)
+    m.bn.running_mean.normal_(0, 0.1); m.bn.running_var.uniform_(0.5, 1.5)
+    m.bn.eps = 1e-3
+    w, b = fold_conv_bn(m.conv, m.bn)
+    w2, b2 = model_ref.fold_bn(m.conv.weight.detach(), m.bn.weight.detach(), m.bn.bias.detach(), m.bn.running_mean, m.bn.running_var)
+    assert torch.allclose(w, w2, atol=1e-6) and torch.allclose(b, b2, atol=1e-6)
+    f = fuse_conv_and_bn(m.conv, m.bn)
+    assert torch.allclose(f.weight, w2, atol=1e-6) and torch.allclose(f.bias, b2, atol=1e-6)
+    x = torch.randn(1, 16, 8, 8)
+    y_ref = F.silu(F.batch_norm(F.conv2d(x, m.conv.weight, None, 1, 1), m.bn.running_mean, m.bn.running_var, m.bn.weight, m.bn.bias, False, 0.0, 1e-3))
+    assert torch.allclose(F.silu(f(x)), y_ref, atol=1e-5)
+
+
+def test_pack_weight_layout():
+    w = torch.arange(2 * 24 * 3 * 3, dtype=torch.float32).view(2, 24, 3, 3)
+    p = pack_weight(w, 32, torch.float16)
+    assert p.shape == (2, 3, 3, 32)
+    assert torch.equal(p[1, 2, 0, :24].float(), w[1, :, 2, 0].half().float())
+    assert torch.count_nonzero(p[..., 24:]) == 0
+
+
+def test_iou_threshold_rule():
+    for t in (0.45, 0.6, 0.5, 0.3, 0.65):
+        f = np.float32(_iou_threshold_f32(t))
+        assert float(f) <= t and float(np.nextafter(f, np.float32(np.inf))) > t
+
+
+def test_cpu_tensors_fail_loudly():
+    m = DetectionModel("yolov5n").eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        C3(16, 16).eval()(torch.zeros(1, 16, 8, 8))
+    from yolov5_b200.utils.general import non_max_suppression
+    from yolov5_b200.utils.metrics import box_iou
+    with pytest.raises(RuntimeError, match="CUDA"):
+        non_max_suppression(torch.zeros(1, 10, 85))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        box_iou(torch.zeros(1, 4), torch.zeros(1, 4))
+
+
+def test_module_pickles_without_engine_state():
+    import pickle
+
+    m = DetectionModel("yolov5n")
+    m.__dict__["_y5_programs"] = {"x": object()}
+    m2 = pickle.loads(pickle.dumps(m))
+    assert "_y5_programs" not in m2.__dict__
+    assert list(m2.state_dict().keys()) == list(m.state_dict().keys())

@@ -1,0 +1,119 @@
+"""CPU: the oracle (oracle/*.py, oracle_c.c) against the golden fixtures produced by the real reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU parity tests then compare the CUDA path with
+the oracle."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import loss_ref, model_ref, nms_ref
+from yolov5_b200.cfg import HYP_SCRATCH_LOW, model_cfg, model_names
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_cfg_tables_match_reference_yaml_digest():
+    ref = json.load(open(os.path.join(G, "cfg_digest.json")))
+    assert set(ref) == set(model_names())
+    for name, digest in ref.items():
+        got = hashlib.sha256(json.dumps(model_cfg(name), sort_keys=True).encode()).hexdigest()
+        assert got == digest, name
+
+
+def _image(shape, seed):
+    return torch.from_numpy(np.random.RandomState(seed).uniform(0, 1, shape).astype(np.float32))
+
+
+def test_model_forward_oracle_vs_reference_outputs():
+    g = np.load(os.path.join(G, "model_forward.npz"))
+    for name in ("yolov5n", "yolov5s", "yolov5n-seg"):
+        cfg = model_cfg(name)
+        seed_w, seed_x = (int(v) for v in g[f"{name}.seed"])
+        sd = model_ref.synth_state_dict(cfg, seed=seed_w)
+        x = _image(tuple(int(v) for v in g[f"{name}.shape"]), seed_x)
+        for tag, fused in (("bn", False), ("fused", True)):
+            with torch.no_grad():
+                out = model_ref.forward(cfg, sd, x, fused=fused)
+            z = out[0].numpy()
+            raws = out[2] if name.endswith("-seg") else out[1]
+            # fp32 CPU conv results may differ in the last bits between machines (threading / mkldnn blocking)
+            np.testing.assert_allclose(z, g[f"{name}.{tag}.z"], rtol=2e-4, atol=2e-4)
+            for l, r in enumerate(raws):
+                np.testing.assert_allclose(r.numpy(), g[f"{name}.{tag}.raw{l}"], rtol=2e-4, atol=2e-4)
+            if name.endswith("-seg"):
+                np.testing.assert_allclose(out[1].numpy(), g[f"{name}.{tag}.proto"], rtol=2e-4, atol=2e-4)
+
+
+def test_model_forward_640_config1_sample():
+    """BASELINE.json configs[0]: yolov5n, 1x3x640x640, CPU fp32."""
+    g = np.load(os.path.join(G, "model_forward.npz"))
+    cfg = model_cfg("yolov5n")
+    sw, sx = (int(v) for v in g["yolov5n.640.seed"])
+    sd = model_ref.synth_state_dict(cfg, seed=sw, head_bias="hot")
+    with torch.no_grad():
+        z = model_ref.forward(cfg, sd, _image((1, 3, 640, 640), sx), fused=True)[0]
+    assert z.shape == (1, 25200, 85)
+    np.testing.assert_allclose(z[0, ::97].numpy(), g["yolov5n.640.z_sample"], rtol=2e-4, atol=2e-4)
+    s = g["yolov5n.640.z_sum"]
+    assert abs(z.double().sum().item() - s[0]) <= 1e-5 * s[1]
+
+
+def test_nms_oracle_bit_exact_vs_golden():
+    g = np.load(os.path.join(G, "nms.npz"))
+    meta = json.loads(str(g["meta"]))
+    assert len(meta) >= 9
+    for c in meta:
+        pred = nms_ref.synth_predictions(c["bs"], c["n"], c["nc"], c["nm"], c["seed"], c["dtype"])
+        out = nms_ref.non_max_suppression(pred, dtype=c["dtype"], **c["kw"])
+        for b, o in enumerate(out):
+            ref = g[f"{c['tag']}.{b}"]
+            assert o.shape == ref.shape, (c["tag"], b)
+            assert np.array_equal(o, ref), (c["tag"], b)
+
+
+def test_nms_greedy_properties():
+    rs = np.random.RandomState(0)
+    xy = rs.uniform(0, 100, (300, 2)).astype(np.float32)
+    wh = rs.uniform(1, 40, (300, 2)).astype(np.float32)
+    boxes = np.concatenate((xy, xy + wh), 1)
+    keep = nms_ref.nms_greedy(boxes, 0.5)
+    assert keep[0] == 0 and np.all(np.diff(keep) > 0)  # first box always kept, order preserved
+    iou = nms_ref.box_iou(boxes[keep], boxes[keep])
+    np.fill_diagonal(iou, 0)
+    assert iou.max() <= 0.5 + 1e-6  # survivors do not suppress each other
+    assert np.array_equal(nms_ref.nms_greedy(boxes[keep], 0.5), np.arange(len(keep)))  # idempotent
+    assert len(nms_ref.nms_greedy(boxes, 0.5, max_keep=7)) == 7
+    assert np.array_equal(nms_ref.nms_greedy(np.zeros((0, 4), np.float32), 0.5), np.zeros(0, np.int64))
+
+
+def test_round_to_matches_torch():
+    x = np.random.RandomState(1).normal(0, 10, 5000).astype(np.float32)
+    t = torch.from_numpy(x)
+    assert np.array_equal(nms_ref.round_to(x, "fp16"), t.half().float().numpy())
+    assert np.array_equal(nms_ref.round_to(x, "bf16"), t.bfloat16().float().numpy())
+
+
+def test_loss_oracle_vs_golden():
+    g = np.load(os.path.join(G, "loss.npz"))
+    cfg = model_cfg("yolov5n")
+    anchors = model_ref.synth_state_dict(cfg, seed=30)["model.24.anchors"].numpy()
+    for tag in ("a", "b", "none"):
+        bs, h, w, seed = (int(v) for v in g[f"{tag}.meta"])
+        rs = np.random.RandomState(seed)
+        p = [torch.from_numpy(rs.normal(0, 1.5, (bs, 3, h // s, w // s, 85)).astype(np.float32)).requires_grad_(True) for s in (8, 16, 32)]
+        tg = loss_ref.synth_targets(bs, seed) if tag != "none" else np.zeros((0, 6), np.float32)
+        bt = loss_ref.build_targets(tg, anchors, [tuple(t.shape[2:4]) for t in p], 4.0)
+        for i in range(3):
+            ref = g[f"{tag}.idx{i}"]
+            got = np.stack([bt[i][k] for k in ("b", "a", "gj", "gi", "tcls")])
+            assert np.array_equal(got, ref), (tag, i)  # integer result: bit exact
+            assert np.array_equal(bt[i]["tbox"], g[f"{tag}.tbox{i}"])
+        loss, items = loss_ref.compute_loss(p, tg, anchors, HYP_SCRATCH_LOW)
+        loss.backward()
+        ref = g[f"{tag}.loss"]
+        np.testing.assert_allclose(np.concatenate((loss.detach().numpy(), items.numpy())), ref, rtol=2e-5, atol=1e-6)
+        gs = np.array([[t.grad.double().sum().item(), t.grad.double().abs().sum().item()] for t in p])
+        np.testing.assert_allclose(gs[:, 1], g[f"{tag}.gradsum"][:, 1], rtol=1e-4)
+        np.testing.assert_allclose(p[0].grad.numpy().reshape(-1)[::1009], g[f"{tag}.grad_sample0"], rtol=1e-4, atol=1e-8)
