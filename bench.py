@@ -1,0 +1,366 @@
+"""bench.py -- images/s of the YOLOv5 inference hot path (forward + non_max_suppression) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload yolov5s|yolov5l|...]
+
+A step = one pass of the hot path over one batch of synthetic images: DetectionModel forward (all conv/C3/SPPF/
+Detect kernels) followed by non_max_suppression, through the public API of yolov5_b200.
+  * N = 1 workload = BASELINE.json configs[1]: yolov5s, bs=32, 640x640, fp16 (+ NMS, detect regime 0.25/0.45).
+  * N > 1: launched by torchrun, one rank per GPU; the path shards over independent images, so every rank runs the
+    same per-GPU batch on its own shard with NO data-path collective ("scaling": "weak"); value = images of all
+    ranks / max-over-ranks time.
+  * value : inputs resident in HBM, CUDA-event timed, barrier + synchronize on both sides.
+  * e2e   : same metric with pinned HOST uint8 batches: every step uploads its batch (H2D) and downloads its
+            detections (D2H) inside the timed region (upload of batch i+1 overlapped with compute of batch i).
+  * roofline : the conv_gemm kernels (tcgen05 implicit GEMM; every Conv/C3/SPPF/Detect launch), timed per launch with
+            CUDA events on the launching stream behind a queued blocker so host launch latency is not in the numbers.
+  * cpu_baseline / --impl reference : the reference's own CPU path.  The reference is pure Python and does not exist
+    on the GPU box, so this is the oracle port (oracle/model_ref.py + oracle/nms_ref.py: the same torch-CPU fp32
+    expressions, pinned to the reference by tests/golden) on all host threads, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {  # name -> (model, per-GPU batch, image size, dtype)
+    "yolov5s": ("yolov5s", 32, 640, "fp16"),   # BASELINE.json configs[1]
+    "yolov5l": ("yolov5l", 64, 640, "bf16"),   # configs[2] at N=1 (per-GPU batch shrinks with N there; here weak)
+    "yolov5n": ("yolov5n", 32, 640, "fp16"),
+    "yolov5m": ("yolov5m", 32, 640, "fp16"),
+    "yolov5x": ("yolov5x", 16, 640, "fp16"),
+}
+NMS_KW = dict(conf_thres=0.25, iou_thres=0.45, max_det=300)  # detect.py regime (reference detect.py:228 defaults)
+TDT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def bench_state_dict(cfg, seed=0, frac=0.02):
+    """Seeded synthetic weights shared by both arms.  Random-init heads emit no NMS candidates (objectness prior
+    ~ sigmoid(-5)), so the Detect biases are calibrated once on the CPU (oracle forward of one seeded image): the
+    objectness bias is shifted so ~`frac` of the anchors pass 0.25 and the class logits are raised (+7) so obj*cls
+    survives too -- synthetic weights only decide how much work NMS sees (~500 candidates / image)."""
+    from oracle import model_ref
+
+    sd = model_ref.synth_state_dict(cfg, seed=seed, head_bias="init")
+    x = torch.from_numpy(np.random.RandomState(seed + 77).uniform(0, 1, (1, 3, 640, 640)).astype(np.float32))
+    threads = torch.get_num_threads()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        raws = model_ref.forward(cfg, sd, x, fused=True)[-1]
+    torch.set_num_threads(threads)
+    nc = cfg["nc"]
+    head = max(int(k.split(".")[1]) for k in sd if k.startswith("model."))
+    for lvl, raw in enumerate(raws):
+        q = torch.quantile(raw[..., 4].flatten(), 1.0 - frac)
+        na = raw.shape[1]
+        b = sd[f"model.{head}.m.{lvl}.bias"].view(na, -1)
+        b[:, 4] += float(-1.0986 - q.item())  # logit(0.25)
+        b[:, 5 : 5 + nc] += 7.0
+    return sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's expressions (oracle port), bounded sample
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_path_once(cfg, sd, x_cpu):
+    from oracle import model_ref, nms_ref
+
+    with torch.no_grad():
+        z = model_ref.forward(cfg, sd, x_cpu, fused=True)[0]
+    return nms_ref.non_max_suppression(z.numpy(), dtype="fp32", **NMS_KW)
+
+
+def cpu_baseline(model_name, size, sample_bs, seed, budget_s=20.0, steps=None, warmup=1):
+    from yolov5_b200.cfg import model_cfg
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_cfg(model_name)
+    sd = bench_state_dict(cfg, seed)
+    x = torch.from_numpy(np.random.RandomState(seed).uniform(0, 1, (sample_bs, 3, size, size)).astype(np.float32))
+    for _ in range(warmup):
+        cpu_path_once(cfg, sd, x)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while (steps is None and time.perf_counter() < t_end and len(times) < 50) or (steps is not None and len(times) < steps):
+        t0 = time.perf_counter()
+        cpu_path_once(cfg, sd, x)
+        times.append(time.perf_counter() - t0)
+        if steps is None and len(times) >= 3 and sum(times) > budget_s:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": sample_bs / (ms / 1e3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} x (forward + NMS) of {sample_bs} images {size}x{size} fp32, oracle port of the reference's "
+                      f"torch-CPU path (reference itself is Python and absent on this box)", "ms_per_step": ms}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("Y5_BENCH_WORKLOAD", "yolov5s"), choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    model_name, bs, size, dt = WORKLOADS[a.workload]
+    if a.batch:
+        bs = a.batch
+    cfg_desc = {"workload": f"{model_name} forward + NMS, bs={bs}/GPU, {size}x{size}, {dt}", "per_gpu_batch": bs,
+                "global_batch": bs * world, "parallelism": f"replicas x{world} (image shards, no collective)",
+                "nms": "conf 0.25 iou 0.45 max_det 300 (detect regime)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        sample_bs = 4
+        cb = cpu_baseline(model_name, size, sample_bs, seed=0, steps=a.steps, warmup=a.warmup)
+        cfg_desc["reference_sample"] = cb["sample"]
+        line = {"impl": "reference", "metric": "images/sec @640 (forward + NMS)", "value": cb["value"], "unit": "images/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch.distributed as dist
+
+    from yolov5_b200 import _lib
+    from yolov5_b200.cfg import model_cfg
+    from yolov5_b200.models.yolo import DetectionModel
+    from yolov5_b200.parallel import aggregate_throughput
+    from yolov5_b200.utils.general import nms_device, non_max_suppression
+
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    cfg = model_cfg(model_name)
+    sd = bench_state_dict(cfg, seed=0)
+    model = DetectionModel(model_name)
+    model.load_state_dict(sd)
+    model = model.to(dev, TDT[dt]).eval()
+    rs = np.random.RandomState(1000 + rank)
+    n_rot = 3  # rotating inputs: 3 x batch > L2 (126 MB) for bs=32 fp16 (236 MB); each step also streams GBs of activations
+    host_u8 = [torch.from_numpy(rs.randint(0, 256, (bs, 3, size, size)).astype(np.uint8)).pin_memory() for _ in range(n_rot)]
+    dev_in = [(h.to(dev).to(TDT[dt]) / 255) for h in host_u8]
+
+    def step(x):
+        z, _ = model(x)
+        return nms_device(z, **NMS_KW)  # device-side result (rows, idx, count): no host sync inside `value`
+
+    for i in range(a.warmup):
+        out = step(dev_in[i % n_rot])
+    torch.cuda.synchronize(dev)
+    cand = int(out[2].sum().item())
+
+    # ---------------- value: device-resident inputs ----------------
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for i in range(a.steps):
+        out = step(dev_in[i % n_rot])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    eager_launches = _lib.launch_count() - l0
+    prog = model._program(dev_in[0])
+    graph_launches = len(prog.ops) * a.steps if prog.graph is not None else 0
+    images, worst_ms = aggregate_throughput(bs * a.steps, ms_total, dev)
+    value = images / (worst_ms / 1e3)
+
+    # ---------------- e2e: pinned host uint8 in, detections out, per step, copy/compute overlapped ----------------
+    copy_s = torch.cuda.Stream(dev)
+    main_s = torch.cuda.current_stream(dev)
+    host_out = torch.empty(bs, NMS_KW["max_det"], 6, dtype=torch.float32).pin_memory()
+    host_cnt = torch.empty(bs, dtype=torch.int32).pin_memory()
+    stage = [torch.empty(bs, 3, size, size, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_run(k):
+        for i in range(k + 1):
+            if i < k:  # upload batch i on the copy stream (uint8: the model scales by 1/255 on the device)
+                with torch.cuda.stream(copy_s):
+                    if i >= 2:
+                        copy_s.wait_event(freed[i % 2])
+                    stage[i % 2].copy_(host_u8[i % n_rot], non_blocking=True)
+                    ready[i % 2].record(copy_s)
+            if i >= 1:  # compute batch i-1
+                j = (i - 1) % 2
+                main_s.wait_event(ready[j])
+                z, _ = model(stage[j])
+                freed[j].record(main_s)
+                rows, _, cnt = nms_device(z, **NMS_KW)
+                host_out.copy_(rows, non_blocking=True)
+                host_cnt.copy_(cnt, non_blocking=True)
+
+    e2e_run(2)
+    barrier()
+    e0.record()
+    e2e_run(a.steps)
+    e1.record()
+    barrier()
+    e2e_images, e2e_ms = aggregate_throughput(bs * a.steps, e0.elapsed_time(e1), dev)
+    h2d = bs * 3 * size * size
+    d2h = host_out.numel() * 4 + host_cnt.numel() * 4
+
+    # ---------------- roofline of the dominant kernel (conv_gemm), per launch, behind a queued blocker ----------------
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        st = _lib.stream_ptr(dev)
+        conv_ops = [op for op in prog.ops if op.fn is prog.lib.y5_conv_plan_run]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prog.ops]
+        reps, conv_ms, all_ms = 3, 0.0, 0.0
+        for _ in range(reps):
+            torch.cuda._sleep(30_000_000)  # ~15 ms of GPU time: the host enqueues everything before the GPU gets to it
+            for op, (s, e) in zip(prog.ops, evs):
+                s.record(); op.run(st); e.record()
+            torch.cuda.synchronize(dev)
+            for op, (s, e) in zip(prog.ops, evs):
+                t = s.elapsed_time(e)
+                all_ms += t
+                if op.fn is prog.lib.y5_conv_plan_run:
+                    conv_ms += t
+        conv_ms /= reps; all_ms /= reps
+        conv_bytes = prog.act_bytes + prog.weight_bytes  # incl. the 3 head GEMMs that run outside `ops` (small)
+        n_conv = len(conv_ops)
+        gbs = conv_bytes / (conv_ms / 1e3) / 1e9
+        tfs = prog.flops / (conv_ms / 1e3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(a.workload)
+        hbm_bound = a.workload in ("yolov5n", "yolov5s", "yolov5m")  # AI below machine balance
+        roof = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all Conv/C3/SPPF launches of one forward)",
+                "bound": "hbm" if hbm_bound else "tensor",
+                "achieved": gbs if hbm_bound else tfs, "peak": pk["hbm"] if hbm_bound else pk["tf_sust"],
+                "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": (gbs / pk["hbm"]) if hbm_bound else (tfs / pk["tf_sust"]),
+                "traffic": traffic, "peak_source": pk["src"] + (" (sustained)" if not hbm_bound else ""),
+                "launches": n_conv, "avg_launch_us": 1e3 * conv_ms / max(n_conv, 1),
+                "algorithmic_bytes_per_launch": conv_bytes / max(n_conv, 1), "flops_per_launch": prog.flops / max(n_conv, 1),
+                "hbm_gbs": gbs, "tensor_tflops": tfs, "tensor_frac_of_sustained": tfs / pk["tf_sust"],
+                "conv_ms_per_forward": conv_ms, "all_fixed_ops_ms_per_forward": all_ms}
+
+    # ---------------- NMS us/img (second half of the metric) ----------------
+    nms_us = None
+    if rank == 0:
+        z, _ = model(dev_in[0])
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(10):
+            nms_device(z, **NMS_KW)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        nms_us = 1e3 * e0.elapsed_time(e1) / 10 / bs
+
+    cb = None
+    if rank == 0 and not a.no_cpu_baseline:
+        cb = cpu_baseline(model_name, size, 4, seed=0, budget_s=15.0)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        cfg_desc.update({"model": model_name, "l2": "3 rotating input batches (> L2 together) and GBs of activations streamed per step",
+                         "weights": "seeded synthetic (oracle.model_ref.synth_state_dict), head bias calibrated to ~2% anchors > 0.25",
+                         "nms_detections_per_batch": cand, "nms_us_per_img": nms_us,
+                         "launches_per_forward": prog.launches_per_forward(), "gflop_per_img": prog.flops / bs / 1e9})
+        line = {"metric": "images/sec @640 (forward + NMS)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": worst_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16" if dt == "fp16" else "bf16", "data": "synthetic", "config": cfg_desc,
+                "clocks": clocks,
+                "e2e": {"value": e2e_images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(eager_launches + graph_launches), "roofline": roof, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,63 @@
+"""GPU: the tcgen05 implicit-GEMM conv (through the C ABI) against the fp32 oracle expression
+SiLU(conv2d(x, W') + b') [+ residual]  (reference models/common.py:86-92,181) on fp16/bf16-rounded operands.
+Tolerance: output is rounded once to fp16 (rel 2^-11) / bf16 (2^-8) after fp32 accumulation -> 2e-3 / 1.6e-2 of max|y|."""
+import pytest
+import torch
+
+from .gpu_util import conv_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}
+
+CASES = [
+    # B, H, W, cin, cout, k, s, p
+    (2, 16, 16, 64, 64, 1, 1, 0),      # plain GEMM, one K block
+    (1, 20, 20, 128, 256, 1, 1, 0),    # M tail (400 rows), N=256
+    (3, 8, 12, 32, 32, 1, 1, 0),       # block_k 32 (SW64), M < 128*? tail
+    (2, 16, 16, 16, 32, 3, 1, 1),      # im2col, block_k 16 (SW32)  -- the stem's shape class
+    (2, 20, 20, 64, 64, 3, 1, 1),      # im2col across rows and images
+    (2, 16, 24, 32, 64, 3, 2, 1),      # stride 2
+    (1, 40, 40, 128, 128, 3, 1, 1),    # 2 K chunks per tap
+    (2, 10, 10, 256, 512, 3, 2, 1),    # deep K (36 blocks), N tiles
+    (2, 12, 12, 24, 48, 1, 1, 0),      # channel count not a multiple of 16 (yolov5m widths): TMA zero-fills K
+    (1, 12, 12, 48, 96, 3, 1, 1),
+    (5, 7, 9, 64, 40, 1, 1, 0),        # odd spatial, N tail inside a tile
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", CASES)
+def test_conv_vs_oracle(cuda, dtype, case):
+    got, ref, _ = conv_case(cuda, dtype, *case)
+    assert rel_err(got, ref) < TOL[dtype], (case, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("case", [(2, 20, 20, 64, 64, 3, 1, 1), (2, 16, 16, 64, 128, 1, 1, 0)])
+def test_conv_residual_and_slices(cuda, case):
+    got, ref, untouched = conv_case(cuda, torch.float16, *case, residual=True, in_extra=24, out_extra=40)
+    assert rel_err(got, ref) < 2e-3
+    assert untouched, "epilogue wrote outside its channel slice"
+
+
+def test_conv_no_activation(cuda):
+    got, ref, _ = conv_case(cuda, torch.float16, 2, 16, 16, 64, 64, 1, 1, 0, act=False)
+    assert rel_err(got, ref) < 2e-3
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+def test_conv_every_tile_width(cuda, bn):
+    got, ref, _ = conv_case(cuda, torch.float16, 2, 20, 20, 64, 256, 3, 1, 1, block_n=bn)
+    assert rel_err(got, ref) < 2e-3
+
+
+def test_tensor_core_path_agrees_with_direct_kernel(cuda):
+    """Two independent device implementations of the same op (tcgen05 GEMM vs CUDA-core direct conv)."""
+    a, ref, _ = conv_case(cuda, torch.float16, 2, 20, 20, 64, 64, 3, 1, 1, seed=5)
+    b, _, _ = conv_case(cuda, torch.float16, 2, 20, 20, 64, 64, 3, 1, 1, seed=5, direct=True)
+    assert rel_err(a, b) < 2e-3 and rel_err(b, ref) < 2e-3
+
+
+def test_large_m_many_tiles_per_cta(cuda):
+    """> 148 tiles so every persistent CTA loops, exercising barrier phase wrap-around."""
+    got, ref, _ = conv_case(cuda, torch.float16, 8, 80, 80, 64, 64, 3, 1, 1)  # 400 M tiles
+    assert rel_err(got, ref) < 2e-3
