@@ -139,7 +139,7 @@ def detect(sd, p, xs, nc, nm, strides, training):
         raw.append(y)
         if training:
             continue
-        gy, gx = torch.meshgrid(torch.arange(ny, dtype=y.dtype), torch.arange(nx, dtype=y.dtype), indexing="ij")
+        gy, gx = torch.meshgrid(torch.arange(ny, dtype=y.dtype, device=y.device), torch.arange(nx, dtype=y.dtype, device=y.device), indexing="ij")
         grid = torch.stack((gx, gy), 2).expand(1, na, ny, nx, 2) - 0.5
         agrid = (anchors[i] * strides[i]).view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2)
         if nm:

@@ -170,6 +170,9 @@ def synth_predictions(bs: int, n_rows: int = 25200, nc: int = 80, nm: int = 0, s
             cls = rs.randint(0, nc)
             r = free[pos : pos + m]
             pos += m
+            m = len(r)
+            if m == 0:
+                break
             x[r, 0:2] = cxy * (1 + rs.uniform(-0.03, 0.03, (m, 2)))
             x[r, 2:4] = wh * (1 + rs.uniform(-0.10, 0.10, (m, 2)))
             x[r, 4] = rs.uniform(0.3, 1.0, m)

@@ -1,0 +1,70 @@
+"""Per-launch timing of one forward program (CUDA events behind a queued blocker) with algorithmic bytes / FLOPs.
+    python tools/layer_profile.py [model] [batch] [size] [dtype]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from yolov5_b200 import _lib, engine
+from yolov5_b200.models.yolo import DetectionModel
+
+name = sys.argv[1] if len(sys.argv) > 1 else "yolov5s"
+bs = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+size = int(sys.argv[3]) if len(sys.argv) > 3 else 640
+dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[sys.argv[4] if len(sys.argv) > 4 else "fp16"]
+dev = torch.device("cuda:0")
+
+# record per-conv metadata by wrapping Program.conv
+meta = {}
+_orig = engine.Program.conv
+
+
+def conv(self, x, out, w, b, k, s, p, act, residual=None, name="conv"):
+    n0 = len(self.ops)
+    _orig(self, x, out, w, b, k, s, p, act, residual, name)
+    m = self.B * out.h * out.w
+    meta[n0] = dict(name=name, M=m, N=out.c, K=x.c * k * k, k=k, s=s, flops=2 * m * out.c * x.c * k * k,
+                    bytes=2 * (self.B * x.h * x.w * x.c + m * out.c) + 2 * out.c * x.c * k * k + (2 * m * out.c if residual is not None else 0))
+
+
+engine.Program.conv = conv
+torch.manual_seed(0)
+m = DetectionModel(name).to(dev, dt).eval()
+x = torch.rand(bs, 3, size, size, device=dev).to(dt)
+prog = m._program(x)
+m(x)
+torch.cuda.synchronize()
+st = _lib.stream_ptr(dev)
+evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prog.ops]
+acc = [0.0] * len(prog.ops)
+reps = 5
+for _ in range(reps):
+    torch.cuda._sleep(40_000_000)
+    for op, (s, e) in zip(prog.ops, evs):
+        s.record(); op.run(st); e.record()
+    torch.cuda.synchronize()
+    for i, (s, e) in enumerate(evs):
+        acc[i] += s.elapsed_time(e) / reps
+tot = sum(acc)
+print(f"{name} bs={bs} {size} {dt}: fixed ops {tot:.3f} ms ({len(prog.ops)} launches)")
+print(f"{'op':28s} {'M':>8s} {'N':>5s} {'K':>5s} {'us':>8s} {'GB/s':>7s} {'TF/s':>6s}  hbm-bound us")
+for i, op in enumerate(prog.ops):
+    md = meta.get(i)
+    if md:
+        us = acc[i] * 1e3
+        print(f"{md['name']:28s} {md['M']:8d} {md['N']:5d} {md['K']:5d} {us:8.1f} {md['bytes'] / us / 1e3:7.0f} {md['flops'] / us / 1e6:6.1f}  {md['bytes'] / 6569e3:8.1f}")
+    else:
+        print(f"{op.name:28s} {'':8s} {'':5s} {'':5s} {acc[i] * 1e3:8.1f}")
+# head + stem timing
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    m(x)
+e1.record()
+torch.cuda.synchronize()
+print(f"full forward (graph + stem + head) {e0.elapsed_time(e1) / 10:.3f} ms")
