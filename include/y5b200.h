@@ -72,6 +72,16 @@ typedef struct y5_conv_desc {
     int32_t dtype;        /* Y5_F16 | Y5_BF16 */
     int32_t block_k;      /* 16|32|64, or 0 = y5_conv_pick's choice; must match the weight packing */
     int32_t block_n;      /* 32|64|128|256, or 0 = auto */
+    /* optional generalisations (all 0 = the plain case above) */
+    int32_t kw;           /* non-square filter: width (height stays `ksize`); 0 = square, and then pad_w is ignored */
+    int32_t pad_w;        /* horizontal padding, only read when kw != 0 (vertical padding stays `pad`) */
+    int64_t in_x_stride;  /* elements between horizontally adjacent pixels (0 = in_pitch).  A stride smaller than in_c
+                             exposes overlapping "wide pixels": the stem runs as a 3x1 conv over 48-channel pixels
+                             that each span 3 neighbouring 16-channel space-to-depth cells */
+    int64_t in_y_stride;  /* elements between rows   (0 = in_w * in_x_stride) */
+    int64_t in_n_stride;  /* elements between images (0 = in_h * in_y_stride) */
+    int32_t a_mode;       /* activation fetch: 0 auto, 1 force TMA-im2col, 2 force shifted-patch (stride-1 only) */
+    int32_t reserved;
 } y5_conv_desc;
 
 /* Tiling the library will use for a conv: block_k decides the weight packing (cin_pad = ceil(in_c/block_k)*block_k). */
@@ -122,9 +132,11 @@ void y5_detect_plan_destroy(y5_detect_plan* plan);
 /* Stem input: NCHW image (Y5_U8 scaled by 1/255, or Y5_F16/Y5_BF16/Y5_F32 already in [0,1]) -> 2x2 space-to-depth
  * NHWC with 16 channels (12 used: (dy*2+dx)*3 + c; 4 zero), so that the 6x6/s2/p2 stem conv of
  * models/yolov5s.yaml:20 becomes a 3x3/s1/p1 conv over 16 channels.  Replaces the `im.half(); im /= 255` of
- * detect.py:206-208 / val.py:259-262 plus the layout change.  h, w even. */
+ * detect.py:206-208 / val.py:259-262 plus the layout change.  h, w even.  `out_row_px` (0 = w/2) is the number of
+ * 16-channel cells per output row of the buffer and `out_x_off` the cell where each row starts: the engine keeps one
+ * zero cell left and right of every row so the stem conv can read 3 neighbouring cells as one 48-channel pixel. */
 int y5_stem_s2d(const void* img, int32_t img_dtype, void* out, int32_t out_dtype, int32_t batch, int32_t h, int32_t w,
-                void* stream);
+                int32_t out_row_px, int32_t out_x_off, void* stream);
 /* SPPF pooling (models/common.py:338-340): reads view x (c channels), writes maxpool5, maxpool5^2 (=9x9),
  * maxpool5^3 (=13x13) into three views (usually channel slices 1..3 of the buffer whose slice 0 is x). */
 int y5_sppf_pool(const void* x, int32_t x_pitch, void* y1, void* y2, void* y3, int32_t y_pitch, int32_t batch, int32_t h,

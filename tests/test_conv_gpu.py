@@ -39,6 +39,17 @@ def test_conv_residual_and_slices(cuda, case):
     assert untouched, "epilogue wrote outside its channel slice"
 
 
+@pytest.mark.parametrize("a_mode", [1, 2])
+@pytest.mark.parametrize("case", [(2, 20, 20, 64, 64, 3, 1, 1), (2, 16, 16, 16, 32, 3, 1, 1), (1, 40, 40, 128, 128, 3, 1, 1),
+                                  (3, 13, 27, 32, 64, 3, 1, 1), (1, 80, 80, 64, 64, 3, 1, 1), (2, 9, 130, 64, 32, 3, 1, 1)])
+def test_conv_3x3_both_fetch_modes(cuda, case, a_mode):
+    """stride-1 3x3: TMA-im2col (one copy per tap) and shifted-patch (one copy per horizontal tap) must agree with the oracle,
+    including partial spatial tiles (13x27, 9x130) and residual + channel-slice views."""
+    got, ref, untouched = conv_case(cuda, torch.float16, *case, a_mode=a_mode, residual=True, in_extra=8, out_extra=24)
+    assert rel_err(got, ref) < 2e-3, (case, a_mode, rel_err(got, ref))
+    assert untouched
+
+
 def test_conv_no_activation(cuda):
     got, ref, _ = conv_case(cuda, torch.float16, 2, 16, 16, 64, 64, 1, 1, 0, act=False)
     assert rel_err(got, ref) < 2e-3

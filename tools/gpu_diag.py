@@ -55,6 +55,16 @@ def s2_im2col():
 
 
 @stage
+def s2b_patch_mode():
+    for a_mode in (1, 2):
+        _conv(f"3x3 s1 a_mode={a_mode}", 2, 20, 20, 64, 64, 3, 1, 1, a_mode=a_mode)
+        _conv(f"3x3 s1 80x80 a_mode={a_mode}", 1, 80, 80, 64, 64, 3, 1, 1, a_mode=a_mode)
+        _conv(f"3x3 s1 13x27 res+slices a_mode={a_mode}", 3, 13, 27, 32, 64, 3, 1, 1, a_mode=a_mode, residual=True, in_extra=8, out_extra=24)
+        _conv(f"3x3 s1 bk16 a_mode={a_mode}", 2, 16, 16, 16, 32, 3, 1, 1, a_mode=a_mode)
+        _conv(f"3x3 s1 9x130 N=32 a_mode={a_mode}", 2, 9, 130, 64, 32, 3, 1, 1, a_mode=a_mode)
+
+
+@stage
 def s3_epilogue_variants():
     import torch
 

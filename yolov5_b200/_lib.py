@@ -35,6 +35,9 @@ class ConvDesc(C.Structure):
         ("residual", C.c_void_p), ("res_pitch", C.c_int32),
         ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("act", C.c_int32), ("dtype", C.c_int32), ("block_k", C.c_int32), ("block_n", C.c_int32),
+        ("kw", C.c_int32), ("pad_w", C.c_int32),
+        ("in_x_stride", C.c_int64), ("in_y_stride", C.c_int64), ("in_n_stride", C.c_int64),
+        ("a_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -88,7 +91,7 @@ SIGNATURES = {
     "y5_detect_plan_run": (_I32, [_P, _P]),
     "y5_detect_plan_run_to": (_I32, [_P, _P, _P, _P]),
     "y5_detect_plan_destroy": (None, [_P]),
-    "y5_stem_s2d": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P]),
+    "y5_stem_s2d": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "y5_sppf_pool": (_I32, [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "y5_upsample2x": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "y5_copy_view": (_I32, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P]),

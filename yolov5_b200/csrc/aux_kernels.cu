@@ -21,7 +21,8 @@ template <> __device__ __forceinline__ float load_px<__nv_bfloat16>(const __nv_b
 template <> __device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
 
 template <typename T>
-__global__ void stem_s2d_kernel(const T* __restrict__ img, uint4* __restrict__ out, int B, int H, int W, int bf16) {
+__global__ void stem_s2d_kernel(const T* __restrict__ img, uint4* __restrict__ out, int B, int H, int W, int bf16, int row_px,
+                                int x_off) {
     const int Wo = W >> 1, Ho = H >> 1;
     const long long total = static_cast<long long>(B) * Ho * Wo;
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -42,8 +43,9 @@ __global__ void stem_s2d_kernel(const T* __restrict__ img, uint4* __restrict__ o
         uint4 lo, hi;
         lo.x = pack2(v[0], v[1], bf16); lo.y = pack2(v[2], v[3], bf16); lo.z = pack2(v[4], v[5], bf16); lo.w = pack2(v[6], v[7], bf16);
         hi.x = pack2(v[8], v[9], bf16); hi.y = pack2(v[10], v[11], bf16); hi.z = pack2(v[12], v[13], bf16); hi.w = pack2(v[14], v[15], bf16);
-        out[idx * 2] = lo;
-        out[idx * 2 + 1] = hi;
+        const long long opx = (static_cast<long long>(b) * Ho + oy) * row_px + x_off + ox;  // row_px >= Wo: zero border columns
+        out[opx * 2] = lo;
+        out[opx * 2 + 1] = hi;
     }
 }
 
@@ -102,6 +104,63 @@ __global__ void sppf_pool_kernel(const uint16_t* __restrict__ x, int x_pitch, ui
         *reinterpret_cast<uint4*>(y1 + o) = pack8(m1, bf16);
         *reinterpret_cast<uint4*>(y2 + o) = pack8(m2, bf16);
         *reinterpret_cast<uint4*>(y3 + o) = pack8(m3, bf16);
+    }
+}
+
+// Shared-memory version: one CTA per (image, 8-channel vector).  The H x W plane of that vector sits in smem
+// (uint4 per pixel) and each k x k / stride-1 max-pool is done separably (row max then column max), three times in a
+// row exactly as the reference chains them; y1, y2, y3 are written as they are produced.  Reads each input element
+// once from HBM and writes 3 outputs: the algorithmic minimum.
+__device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b, bool bf16) {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (bf16) {
+            __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]), *reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+            o[j] = *reinterpret_cast<uint32_t*>(&r);
+        } else {
+            __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&aw[j]), *reinterpret_cast<const __half2*>(&bw[j]));
+            o[j] = *reinterpret_cast<uint32_t*>(&r);
+        }
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void sppf_pool_smem_kernel(const uint16_t* __restrict__ x, int x_pitch, uint16_t* y1, uint16_t* y2, uint16_t* y3,
+                                      int y_pitch, int H, int W, int C, int k, int bf16) {
+    extern __shared__ uint4 plane[];  // [2][H*W]
+    const int cv = C >> 3;
+    const int b = blockIdx.x / cv, c8 = blockIdx.x - b * cv;
+    const int HW = H * W, r = k / 2;
+    uint4* cur = plane;
+    uint4* tmp = plane + HW;
+    const long long base = static_cast<long long>(b) * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) cur[i] = *reinterpret_cast<const uint4*>(x + (base + i) * x_pitch + c8 * 8);
+    __syncthreads();
+    uint16_t* outs[3] = {y1, y2, y3};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // row max
+            const int py = i / W, px = i - py * W;
+            uint4 m = cur[i];
+            for (int d = 1; d <= r; ++d) {
+                if (px - d >= 0) m = max8(m, cur[i - d], bf16);
+                if (px + d < W) m = max8(m, cur[i + d], bf16);
+            }
+            tmp[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // column max
+            const int py = i / W;
+            uint4 m = tmp[i];
+            for (int d = 1; d <= r; ++d) {
+                if (py - d >= 0) m = max8(m, tmp[i - d * W], bf16);
+                if (py + d < H) m = max8(m, tmp[i + d * W], bf16);
+            }
+            cur[i] = m;  // safe: this pass reads only tmp
+            *reinterpret_cast<uint4*>(outs[pass] + (base + i) * y_pitch + c8 * 8) = m;
+        }
+        __syncthreads();
     }
 }
 
@@ -173,7 +232,9 @@ static int check_launch(const char* what) {
 static bool half_dtype(int d) { return d == Y5_F16 || d == Y5_BF16; }
 
 extern "C" Y5_API int y5_stem_s2d(const void* img, int32_t img_dtype, void* out, int32_t out_dtype, int32_t batch, int32_t h, int32_t w,
-                           void* stream) {
+                                  int32_t out_row_px, int32_t out_x_off, void* stream) {
+    const int row_px = out_row_px > 0 ? out_row_px : w / 2;
+    if (out_x_off < 0 || out_x_off + w / 2 > row_px) return set_error(Y5_E_INVALID, "stem_s2d: output row pitch/offset do not cover the row");
     if (!img || !out || batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return set_error(Y5_E_INVALID, "stem_s2d: bad arguments (h, w must be even)");
     if (!half_dtype(out_dtype)) return set_error(Y5_E_UNSUPPORTED, "stem_s2d: output dtype must be fp16/bf16");
     const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2);
@@ -182,10 +243,10 @@ extern "C" Y5_API int y5_stem_s2d(const void* img, int32_t img_dtype, void* out,
     const int bf = out_dtype == Y5_BF16;
     uint4* o = static_cast<uint4*>(out);
     switch (img_dtype) {
-        case Y5_U8: stem_s2d_kernel<uint8_t><<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(img), o, batch, h, w, bf); break;
-        case Y5_F16: stem_s2d_kernel<__half><<<grid, threads, 0, st>>>(static_cast<const __half*>(img), o, batch, h, w, bf); break;
-        case Y5_BF16: stem_s2d_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(img), o, batch, h, w, bf); break;
-        case Y5_F32: stem_s2d_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(img), o, batch, h, w, bf); break;
+        case Y5_U8: stem_s2d_kernel<uint8_t><<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(img), o, batch, h, w, bf, row_px, out_x_off); break;
+        case Y5_F16: stem_s2d_kernel<__half><<<grid, threads, 0, st>>>(static_cast<const __half*>(img), o, batch, h, w, bf, row_px, out_x_off); break;
+        case Y5_BF16: stem_s2d_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(img), o, batch, h, w, bf, row_px, out_x_off); break;
+        case Y5_F32: stem_s2d_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(img), o, batch, h, w, bf, row_px, out_x_off); break;
         default: return set_error(Y5_E_UNSUPPORTED, "stem_s2d: image dtype %d", img_dtype);
     }
     return check_launch("stem_s2d");
@@ -195,6 +256,15 @@ extern "C" Y5_API int y5_sppf_pool(const void* x, int32_t x_pitch, void* y1, voi
                             int32_t w, int32_t c, int32_t ksize, int32_t dtype, void* stream) {
     if (!x || !y1 || !y2 || !y3 || batch <= 0 || h <= 0 || w <= 0 || c <= 0) return set_error(Y5_E_INVALID, "sppf_pool: bad arguments");
     if (c % 8 || x_pitch % 8 || y_pitch % 8 || !half_dtype(dtype) || !(ksize & 1)) return set_error(Y5_E_UNSUPPORTED, "sppf_pool: c/pitch %% 8, odd k, fp16/bf16 only");
+    const size_t smem = static_cast<size_t>(2) * h * w * sizeof(uint4);
+    if (smem <= 96 * 1024 && static_cast<long long>(batch) * (c / 8) < 0x7fffffff) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(sppf_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+        sppf_pool_smem_kernel<<<batch * (c / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const uint16_t*>(x), x_pitch, static_cast<uint16_t*>(y1), static_cast<uint16_t*>(y2), static_cast<uint16_t*>(y3),
+            y_pitch, h, w, c, ksize, dtype == Y5_BF16);
+        return check_launch("sppf_pool");
+    }
     const long long total = static_cast<long long>(batch) * h * w * (c / 8);
     const int threads = 128, grid = grid_for(total, threads);
     sppf_pool_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -136,11 +136,18 @@ class Program:
 
     # ------------------------------------------------------------------ op emitters
     def conv(self, x: View, out: View, w_fp32: torch.Tensor, b_fp32: torch.Tensor, k: int, s: int, p: int, act: bool,
-             residual: View | None = None, name: str = "conv"):
-        cin, cout = x.c, out.c
-        assert w_fp32.shape == (cout, cin, k, k), (w_fp32.shape, cout, cin, k)
-        ho = (x.h + 2 * p - k) // s + 1
-        wo = (x.w + 2 * p - k) // s + 1
+             residual: View | None = None, name: str = "conv", virt=None):
+        """Emit one fused conv.  `virt` (stem only) = dict(ptr, in_c, in_w, in_h, x_stride, y_stride, n_stride, kw, pad_w):
+        a strided "wide pixel" view of the input and a non-square filter, see y5_conv_desc in include/y5b200.h."""
+        cout = out.c
+        if virt is None:
+            cin, in_h, in_w, kw = x.c, x.h, x.w, k
+            assert w_fp32.shape == (cout, cin, k, k), (w_fp32.shape, cout, cin, k)
+            ho, wo = (x.h + 2 * p - k) // s + 1, (x.w + 2 * p - k) // s + 1
+        else:
+            cin, in_h, in_w, kw = virt["in_c"], virt["in_h"], virt["in_w"], virt["kw"]
+            assert w_fp32.shape == (cout, cin, k, kw), (w_fp32.shape, cout, cin, k, kw)
+            ho, wo = (in_h + 2 * p - k) // s + 1, (in_w + 2 * virt["pad_w"] - kw) // s + 1
         assert (ho, wo) == (out.h, out.w), (name, ho, wo, out.h, out.w)
         m_rows = self.B * ho * wo
         bk, bn = C.c_int32(), C.c_int32()
@@ -152,8 +159,13 @@ class Program:
         bias = b_fp32.to(torch.float32).contiguous()
         self._keep += [wp, bias]
         d = ConvDesc()
-        d.inp, d.in_pitch = x.ptr, x.pitch
-        d.batch, d.in_h, d.in_w, d.in_c = self.B, x.h, x.w, cin
+        if virt is None:
+            d.inp, d.in_pitch = x.ptr, x.pitch
+        else:
+            d.inp, d.in_pitch = virt["ptr"], virt["x_stride"]
+            d.in_x_stride, d.in_y_stride, d.in_n_stride = virt["x_stride"], virt["y_stride"], virt["n_stride"]
+            d.kw, d.pad_w = kw, virt["pad_w"]
+        d.batch, d.in_h, d.in_w, d.in_c = self.B, in_h, in_w, cin
         d.weight, d.bias = wp.data_ptr(), bias.data_ptr()
         d.out, d.out_pitch, d.out_c = out.ptr, out.pitch, cout
         d.residual = residual.ptr if residual is not None else None
@@ -161,13 +173,17 @@ class Program:
         d.ksize, d.stride, d.pad = k, s, p
         d.act = _lib.ACT_SILU if act else _lib.ACT_NONE
         d.dtype, d.block_k, d.block_n = self.dt_code, bk.value, bn.value
+        d.a_mode = int(os.environ.get("Y5_FORCE_A_MODE", "0"))
+        if d.a_mode == 2 and s != 1:
+            d.a_mode = 0
         plan = C.c_void_p()
         _lib.check(self.lib.y5_conv_plan_create(C.byref(d), C.byref(plan)), f"conv_plan_create[{name}]")
         self._plans.append((self.lib.y5_conv_plan_destroy, plan))
         self.ops.append(_Op(name, self.lib.y5_conv_plan_run, (plan,)))
-        self.flops += 2 * m_rows * cout * cin * k * k
-        self.act_bytes += 2 * (self.B * x.h * x.w * cin + m_rows * cout)
-        self.weight_bytes += 2 * cout * cin * k * k
+        if virt is None:
+            self.flops += 2 * m_rows * cout * cin * k * k
+            self.act_bytes += 2 * (self.B * x.h * x.w * x.c + m_rows * cout)
+            self.weight_bytes += 2 * cout * cin * k * k
 
     def conv_module(self, m, x: View, out: View, residual: View | None = None, name="conv"):
         """m: models.common.Conv (conv + bn + act) in its fused or unfused state."""
@@ -194,11 +210,33 @@ class Program:
                 raise NotImplementedError("y5b200: the first layer must be the YOLOv5 v6 stem Conv(3, c, 6, 2, 2)")
             if self.H % 2 or self.W % 2:
                 raise ValueError("y5b200: image height and width must be even")
-            s2d = self.new_view(self.H // 2, self.W // 2, 16)
-            self.stem_in = s2d
+            h2, w2 = self.H // 2, self.W // 2
+            # space-to-depth buffer with one zero cell left and right of every row: [B][h2][w2+2][16]
+            s2d_buf = torch.zeros(self.B, h2, w2 + 2, 16, dtype=self.dtype, device=self.device)
+            self._keep.append(s2d_buf)
+            self.stem_in = s2d_buf
             w, b = fold_conv_bn(m.conv, getattr(m, "bn", None))
-            out = out or self.new_view(self.H // 2, self.W // 2, m.conv.out_channels)
-            self.conv(s2d, out, stem_weight_s2d(w), b, 3, 1, 1, isinstance(m.act, torch.nn.SiLU), None, name)
+            out = out or self.new_view(h2, w2, m.conv.out_channels)
+            w3 = stem_weight_s2d(w)  # (O,16,3,3): 3x3/s1/p1 over the 16-channel cells
+            act = isinstance(m.act, torch.nn.SiLU)
+            # 3 horizontally adjacent cells are contiguous in memory (48 channels): run the stem as a 3x1 conv over
+            # overlapping 48-channel "wide pixels" (x stride 16 elements) -> 3 taps of K=48 instead of 9 taps of K=16
+            wv = w3.permute(0, 3, 1, 2).reshape(w3.shape[0], 48, 3, 1)  # [o][s*16+c][r][0] = w3[o][c][r][s]
+            virt = dict(ptr=s2d_buf.data_ptr(), in_c=48, in_w=w2, in_h=h2, x_stride=16, y_stride=(w2 + 2) * 16,
+                        n_stride=h2 * (w2 + 2) * 16, kw=1, pad_w=0)
+            n_before = len(self.ops)
+            try:
+                self.conv(None, out, wv, b, 3, 1, 1, act, None, name + "(s2d 3x1x48)", virt=virt)
+            except RuntimeError:
+                # driver refused the overlapping-stride tensor map: plain 3x3 over 16-channel cells of the padded buffer
+                del self.ops[n_before:]
+                virt = dict(ptr=s2d_buf.data_ptr() + 16 * s2d_buf.element_size(), in_c=16, in_w=w2, in_h=h2, x_stride=16,
+                            y_stride=(w2 + 2) * 16, n_stride=h2 * (w2 + 2) * 16, kw=3, pad_w=1)
+                self.conv(None, out, w3, b, 3, 1, 1, act, None, name + "(s2d 3x3x16)", virt=virt)
+            cout = m.conv.out_channels
+            self.flops += 2 * self.B * h2 * w2 * cout * 3 * 36
+            self.act_bytes += 2 * (self.B * self.H * self.W * 3 + self.B * h2 * w2 * cout)
+            self.weight_bytes += 2 * cout * 3 * 36
             return out
         ho, wo = self.out_hw(m, x)
         out = out or self.new_view(ho, wo, m.conv.out_channels)
@@ -258,11 +296,18 @@ class Program:
         row0 = 0
         for i, v in enumerate(xs):
             conv = m.m[i]
-            w = conv.weight.detach().float()
+            HEAD_N = 128  # kHeadN in conv_gemm.cu: one anchor per 128-wide N tile
+            if no > HEAD_N:
+                raise NotImplementedError(f"y5b200: Detect with no={no} > {HEAD_N} outputs per anchor")
+            w = conv.weight.detach().float()  # (na*no, C, 1, 1)
             bk = C.c_int32()
             _lib.check(self.lib.y5_conv_pick(v.c, na * no, self.B * v.h * v.w, C.byref(bk), None), "conv_pick")
-            wp = pack_weight(w, bk.value, self.dtype)
-            bias = conv.bias.detach().float().contiguous()
+            wpad = torch.zeros(na, HEAD_N, v.c, 1, 1, dtype=w.dtype, device=w.device)
+            wpad[:, :no] = w.view(na, no, v.c, 1, 1)
+            wp = pack_weight(wpad.view(na * HEAD_N, v.c, 1, 1), bk.value, self.dtype)
+            bias = torch.zeros(na, HEAD_N, dtype=torch.float32, device=w.device)
+            bias[:, :no] = conv.bias.detach().float().view(na, no)
+            bias = bias.view(-1).contiguous()
             self._keep += [wp, bias]
             d = DetectDesc()
             d.inp, d.in_pitch = v.ptr, v.pitch
@@ -433,8 +478,8 @@ class Program:
         if not img.is_contiguous():
             img = img.contiguous()
         st = _lib.stream_ptr(self.device)
-        _lib.check(self.lib.y5_stem_s2d(img.data_ptr(), _lib.dtype_code(img.dtype), self.stem_in.ptr, self.dt_code, self.B, self.H,
-                                        self.W, C.c_void_p(st)), "stem_s2d")
+        _lib.check(self.lib.y5_stem_s2d(img.data_ptr(), _lib.dtype_code(img.dtype), self.stem_in.data_ptr(), self.dt_code, self.B,
+                                        self.H, self.W, self.W // 2 + 2, 1, C.c_void_p(st)), "stem_s2d")
         if use_graph and os.environ.get("Y5_NO_GRAPH") != "1":
             if self.graph is None:
                 self.capture()
