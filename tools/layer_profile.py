@@ -23,12 +23,16 @@ meta = {}
 _orig = engine.Program.conv
 
 
-def conv(self, x, out, w, b, k, s, p, act, residual=None, name="conv"):
+def conv(self, x, out, w, b, k, s, p, act, residual=None, name="conv", virt=None):
     n0 = len(self.ops)
-    _orig(self, x, out, w, b, k, s, p, act, residual, name)
+    _orig(self, x, out, w, b, k, s, p, act, residual, name, virt)
     m = self.B * out.h * out.w
-    meta[n0] = dict(name=name, M=m, N=out.c, K=x.c * k * k, k=k, s=s, flops=2 * m * out.c * x.c * k * k,
-                    bytes=2 * (self.B * x.h * x.w * x.c + m * out.c) + 2 * out.c * x.c * k * k + (2 * m * out.c if residual is not None else 0))
+    if virt is None:
+        cin, kk, in_el = x.c, k * k, self.B * x.h * x.w * x.c
+    else:  # stem: count the real 6x6x3 filter and the image
+        cin, kk, in_el = 3, 36, self.B * self.H * self.W * 3
+    meta[n0] = dict(name=name, M=m, N=out.c, K=cin * kk, k=k, s=s, flops=2 * m * out.c * cin * kk,
+                    bytes=2 * (in_el + m * out.c) + 2 * out.c * cin * kk + (2 * m * out.c if residual is not None else 0))
 
 
 engine.Program.conv = conv

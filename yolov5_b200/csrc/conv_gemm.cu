@@ -15,12 +15,16 @@
 // MMA: one elected thread issues tcgen05.mma (M128 x BLOCK_N x K16, fp32 accumulate) into one of two TMEM
 // accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1; tcgen05.commit releases smem stages and
 // publishes the accumulator.
-// Epilogue (8 warps): tcgen05.ld -> + folded-BN bias -> SiLU -> (+ residual) -> fp16/bf16 -> swizzled smem staging ->
-// ONE TMA store per 64-channel slab (2-D for linear tiles, 4-D for spatial tiles; row/column tails and channel-slice
-// pitches are clipped/handled by the tensor map).  Detect head (EPI=1): N tile == one anchor; raw logits and decoded
-// predictions are staged in the exact global layout and copied out with 16-byte vectors.
+// Tiles: every tile owns 128 TMEM columns = MT sub-tiles of 128 rows x BLOCK_N (MT = 128/BLOCK_N for BLOCK_N < 128), so
+// narrow layers amortise the per-tile latencies like wide ones and one B tile feeds MT sub-tiles.
+// Epilogue (16 independent warps, no block barrier): warp = (TMEM lane quarter, slot); each drains its 32-column chunks
+// with tcgen05.ld -> + folded-BN bias (whole vector preloaded in smem) -> SiLU -> (+ residual, prefetched into
+// registers before the TMEM load) -> fp16/bf16 -> 64 contiguous bytes per row straight to the NHWC (slice) view, then
+// arrives on the accumulator's "empty" barrier and moves on to the next tile while its siblings may still be storing.
+// Detect head (EPI=1): N tile == one anchor; raw logits and decoded predictions are staged in smem in the exact
+// global layout and copied out with 16-byte vectors.
 // Persistent grid (<= one CTA per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2..9 epilogue.
+// warps 2..17 epilogue.
 //
 // Replaces reference models/common.py:86-92 (Conv), :181 (Bottleneck add), :246/:340/:453 (cat, via strided
 // output views) and models/yolo.py:95-113 (Detect level).
@@ -35,31 +39,39 @@
 namespace y5 {
 
 constexpr int kBlockM = 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;  // warp0 producer, warp1 mma, warps 2..9 epilogue
+constexpr int kThreads = 64 + kEpiThreads;  // warp0 producer, warp1 mma, warps 2..17 epilogue
 constexpr int kMaxStages = 8;
 constexpr int kHeadN = 128;                 // head GEMM: one anchor per 128-wide N tile (no <= 128)
 
 enum AMode { A_LINEAR = 0, A_IM2COL = 1, A_PATCH = 2 };
 
+// sub-tiles (128 rows each) per tile: every tile owns 128 TMEM columns (256 for BLOCK_N = 256), so the fixed per-tile
+// latencies (barrier round trips, TMEM load, first global access) are amortised over the same amount of output whatever
+// the channel count, and one B tile feeds MT sub-tiles.
+__host__ __device__ constexpr int mt_for(int block_n, int epi) { return (epi == 0 && block_n < 128) ? 128 / block_n : 1; }
+
 struct ConvParams {
     int M, N;                   // GEMM rows (B*Ho*Wo), output channels
-    int num_m_tiles, num_n_tiles;
+    int num_m_tiles;            // 128-row sub-tiles
+    int num_m_super, num_n_tiles;
     int kh, kw, c_chunks;       // K loop = kh*kw*c_chunks blocks of block_k
     int block_k;                // 16 | 32 | 64 elements (row bytes 32/64/128)
     int a_mode;
     int Ho, Wo, HoWo, stride, pad_h, pad_w;
-    int tw, th, tiles_x, tiles_y;  // PATCH: spatial tile th x tw (= 128 pixels), tiles per image
+    int tw, th, tiles_x, tiles_y;  // PATCH: spatial sub-tile th x tw (= 128 pixels), sub-tiles per image
     int a_stages, b_stages;
-    uint32_t a_stage_bytes, b_stage_bytes;
+    uint32_t a_sub_bytes, a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
     int is_bf16, act;
     const float* bias;
+    int bias_n;                 // floats preloaded into smem
     // EPI 0
+    void* out;
+    int out_pitch;
     const void* res;
     int res_pitch;
-    int out_slab_c;             // channels per TMA-store slab (64, or 32 when BLOCK_N == 32)
     // EPI 1 (detect head)
     void* raw;
     void* z;
@@ -72,11 +84,7 @@ struct SmemLayout {
     uint32_t off_a, off_b, off_out, off_bias, off_bars, off_tmem, total;
 };
 
-__host__ __device__ inline uint32_t out_stage_bytes(int block_n, int epi, int no) {
-    return epi == 1 ? ((kBlockM * no * 2 + 1023) & ~1023u) : kBlockM * block_n * 2;
-}
-
-__host__ __device__ inline SmemLayout smem_layout(int block_n, int epi, int no, int a_stages, int b_stages, uint32_t a_bytes,
+__host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, int a_stages, int b_stages, uint32_t a_bytes,
                                                    uint32_t b_bytes) {
     SmemLayout L;
     uint32_t o = 0;
@@ -86,9 +94,9 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int epi, int no, 
     o += b_stages * b_bytes;
     o = (o + 1023) & ~1023u;
     L.off_out = o;
-    o += out_stage_bytes(block_n, epi, no);
+    if (epi == 1) o += (kBlockM * no * 2 + 1023) & ~1023u;  // head: one anchor's [128][no] block in its global layout
     L.off_bias = o;
-    o += block_n * 4;
+    o += ((bias_n + 3) & ~3) * 4;
     o = (o + 7) & ~7u;
     L.off_bars = o;
     o += (4 * kMaxStages + 4) * 8;
@@ -98,22 +106,20 @@ __host__ __device__ inline SmemLayout smem_layout(int block_n, int epi, int no, 
     return L;
 }
 
-// byte offset inside a swizzled smem tile whose rows are `row_bytes` wide (Swizzle<B,4,3>: 16-B chunk index XOR row bits)
-__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t row_bytes) {
-    const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
-    return off ^ (((off >> 7) & mask) << 4);
-}
-
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    constexpr int MT = mt_for(BLOCK_N, EPI);
+    constexpr int kAccCols = MT * BLOCK_N;          // TMEM columns per accumulator set (128 or 256)
+    constexpr uint32_t kTmemCols = 2 * kAccCols;    // two sets: epilogue of tile i overlaps the MMAs of tile i+1
+    constexpr int kChunks = kAccCols / 32;          // 32-column epilogue work items per tile (4 or 8)
+    constexpr int kChunksPerSub = BLOCK_N / 32;
+
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemLayout L = smem_layout(BLOCK_N, EPI, p.no, p.a_stages, p.b_stages, p.a_stage_bytes, p.b_stage_bytes);
+    const SmemLayout L = smem_layout(EPI, p.no, p.bias_n, p.a_stages, p.b_stages, p.a_stage_bytes, p.b_stage_bytes);
     uint8_t* sA = smem + L.off_a;
     uint8_t* sB = smem + L.off_b;
-    uint8_t* sOut = smem + L.off_out;
     float* sBias = reinterpret_cast<float*>(smem + L.off_bias);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint64_t* a_empty = a_full + kMaxStages;
@@ -125,12 +131,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if (EPI == 0) tma_prefetch_desc(&tmO);
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
@@ -144,12 +148,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp >= 2)  // whole folded-BN bias vector once: no per-tile global loads on the epilogue's critical path
+        for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) sBias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = p.num_m_super * p.num_n_tiles;
     const uint32_t row_bytes = p.block_k * 2;
     const bool patch = p.a_mode == A_PATCH;
     // K iteration: "A groups" each feeding `grp` consecutive B tiles.
@@ -164,23 +170,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile / p.num_n_tiles;
+                const int ms = tile / p.num_n_tiles;
                 const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-                int img = 0, y0 = 0, x0 = 0;  // IM2COL: base pixel of the first window; PATCH: tile origin
-                if (p.a_mode == A_IM2COL) {
-                    const int m0 = mt * kBlockM;
-                    img = m0 / p.HoWo;
-                    const int rem = m0 - img * p.HoWo;
-                    const int oy = rem / p.Wo;
-                    y0 = oy * p.stride - p.pad_h;
-                    x0 = (rem - oy * p.Wo) * p.stride - p.pad_w;
-                } else if (patch) {
-                    const int per_img = p.tiles_x * p.tiles_y;
-                    img = mt / per_img;
-                    const int rem = mt - img * per_img;
-                    const int ty = rem / p.tiles_x;
-                    y0 = ty * p.th - p.pad_h;
-                    x0 = (rem - ty * p.tiles_x) * p.tw - p.pad_w;
+                int img[MT], y0[MT], x0[MT];  // IM2COL: base pixel of the first window; PATCH: sub-tile origin
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) {
+                    const int mt = ms * MT + mi;
+                    img[mi] = y0[mi] = x0[mi] = 0;
+                    if (p.a_mode == A_IM2COL) {
+                        const int m0 = mt * kBlockM;
+                        img[mi] = m0 / p.HoWo;
+                        const int rem = m0 - img[mi] * p.HoWo;
+                        const int oy = rem / p.Wo;
+                        y0[mi] = oy * p.stride - p.pad_h;
+                        x0[mi] = (rem - oy * p.Wo) * p.stride - p.pad_w;
+                    } else if (patch) {
+                        const int per_img = p.tiles_x * p.tiles_y;
+                        img[mi] = mt / per_img;
+                        const int rem = mt - img[mi] * per_img;
+                        const int ty = rem / p.tiles_x;
+                        y0[mi] = ty * p.th - p.pad_h;
+                        x0[mi] = (rem - ty * p.tiles_x) * p.tw - p.pad_w;
+                    }
                 }
                 for (int g = 0; g < num_groups; ++g) {
                     int cc, s, r0;
@@ -188,12 +199,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else { const int t = g / p.c_chunks; cc = g - t * p.c_chunks; r0 = t / p.kw; s = t - r0 * p.kw; }
                     mbar_wait(&a_empty[as], aph ^ 1);
                     mbar_arrive_expect_tx(&a_full[as], p.a_stage_bytes);
-                    uint8_t* a_dst = sA + as * p.a_stage_bytes;
-                    if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, mt * kBlockM);
-                    else if (p.a_mode == A_IM2COL)
-                        tma_load_im2col_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0, y0, img, static_cast<uint16_t>(s),
-                                           static_cast<uint16_t>(r0));
-                    else tma_load_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0 + s, y0, img);
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi) {
+                        uint8_t* a_dst = sA + as * p.a_stage_bytes + mi * p.a_sub_bytes;
+                        if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
+                        else if (p.a_mode == A_IM2COL)
+                            tma_load_im2col_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
+                                               static_cast<uint16_t>(s), static_cast<uint16_t>(r0));
+                        else tma_load_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi] + s, y0[mi], img[mi]);
+                    }
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                     for (int j = 0; j < grp; ++j) {
                         const int r = patch ? j : r0;
@@ -216,7 +230,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                const uint32_t d_tmem = tmem_base + acc * kAccCols;
                 uint32_t accum = 0;
                 for (int g = 0; g < num_groups; ++g) {
                     mbar_wait(&a_full[as], aph);
@@ -226,9 +240,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tc_fence_after();
                         const uint32_t b_addr = smem_u32(sB + bs * p.b_stage_bytes);
                         for (int k = 0; k < k_steps; ++k) {
-                            const uint64_t ad = umma_smem_desc(a_addr + j * a_shift + k * 32, row_bytes);
                             const uint64_t bd = umma_smem_desc(b_addr + k * 32, row_bytes);
-                            umma_f16_ss(d_tmem, ad, bd, p.idesc, accum);
+#pragma unroll
+                            for (int mi = 0; mi < MT; ++mi) {
+                                const uint64_t ad = umma_smem_desc(a_addr + mi * p.a_sub_bytes + j * a_shift + k * 32, row_bytes);
+                                umma_f16_ss(d_tmem + mi * BLOCK_N, ad, bd, p.idesc, accum);
+                            }
                             accum = 1;
                         }
                         umma_commit(&b_empty[bs]);
@@ -242,73 +259,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ===================================== epilogue (warps 2..9) =====================================
-        const int et = threadIdx.x - 64;          // 0..255
-        const int ew = warp - 2;                  // 0..7
+        // ===================================== epilogue (warps 2..17) =====================================
+        // 16 independent warps: warp = (TMEM lane quarter, slot); slot s drains the 32-column chunks s, s+4, ...
+        // of every tile straight to global memory.  No block-level barrier: a warp that is done with tile i moves
+        // on to tile i+1 (other accumulator set) while its siblings may still be storing.
+        const int et = threadIdx.x - 64;          // 0..511
+        const int ew = warp - 2;                  // 0..15
         const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                 // two warps share a quarter: they split the 32-column chunks
+        const int slot = ew >> 2;                 // 0..3
         const int row = quarter * 32 + lane;      // accumulator row (= TMEM lane) owned by this thread
         const bool bf16 = p.is_bf16 != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / p.num_n_tiles;
+            const int ms = tile / p.num_n_tiles;
             const int nt = tile % p.num_n_tiles;
             const int n0 = nt * BLOCK_N;
-            // global pixel index of this thread's row (residual / head addressing); -1 = outside the tensor
-            long long gpix = -1;
-            int img = 0, pix = 0, oy0 = 0, ox0 = 0;
-            if (patch) {
-                const int per_img = p.tiles_x * p.tiles_y;
-                img = mt / per_img;
-                const int rem = mt - img * per_img;
-                const int tyi = rem / p.tiles_x;
-                oy0 = tyi * p.th;
-                ox0 = (rem - tyi * p.tiles_x) * p.tw;
-                const int ry = row / p.tw, rx = row - ry * p.tw;
-                if (oy0 + ry < p.Ho && ox0 + rx < p.Wo) {
-                    pix = (oy0 + ry) * p.Wo + ox0 + rx;
-                    gpix = static_cast<long long>(img) * p.HoWo + pix;
-                }
-            } else {
-                const int m = mt * kBlockM + row;
-                if (m < p.M) {
-                    gpix = m;
-                    img = m / p.HoWo;
-                    pix = m - img * p.HoWo;
-                }
-            }
-            // the previous tile's TMA store must have finished READING the staging buffer before it is overwritten
-            if (EPI == 0 && et == 0) tma_store_wait_read0();
-            named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < BLOCK_N; i += kEpiThreads) sBias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
-            named_bar_sync(1, kEpiThreads);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
 
             if (EPI == 0) {
-                const uint8_t* res_row =
-                    (p.res && gpix >= 0) ? reinterpret_cast<const uint8_t*>(p.res) + static_cast<size_t>(gpix) * p.res_pitch * 2 : nullptr;
-                const uint32_t slab_row_bytes = p.out_slab_c * 2;           // 128 (64 ch) or 64 (32 ch)
-                const uint32_t slab_bytes = kBlockM * slab_row_bytes;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll 1
-                for (int c = half; c < BLOCK_N / 32; c += 2) {
+                for (int c = slot; c < kChunks; c += 4) {
+                    const int mi = c / kChunksPerSub;             // sub-tile of this chunk
+                    const int col = (c - mi * kChunksPerSub) * 32;  // first column inside the N tile
+                    const int mt = ms * MT + mi;
+                    long long gpix = -1;                          // global output pixel of this thread's row
+                    if (patch) {
+                        const int per_img = p.tiles_x * p.tiles_y;
+                        const int img = mt / per_img;
+                        const int rem = mt - img * per_img;
+                        const int tyi = rem / p.tiles_x;
+                        const int oy = tyi * p.th + row / p.tw, ox = (rem - tyi * p.tiles_x) * p.tw + row % p.tw;
+                        if (mt < p.num_m_tiles && oy < p.Ho && ox < p.Wo) gpix = static_cast<long long>(img) * p.HoWo + oy * p.Wo + ox;
+                    } else {
+                        const long long m = static_cast<long long>(mt) * kBlockM + row;
+                        if (m < p.M) gpix = m;
+                    }
+                    const bool live = gpix >= 0;
+                    // residual for this thread's 32 output channels: issued before the TMEM load so its latency overlaps
+                    uint4 rv[4];
+                    const bool has_res = p.res != nullptr && live;
+                    if (has_res) {
+                        const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (gpix * p.res_pitch + n0 + col) * 2;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (n0 + col + g * 8 < p.N) rv[g] = *reinterpret_cast<const uint4*>(rp + g * 16);
+                    }
                     uint32_t v[32];
                     tmem_ld_32x32(t_row + c * 32, v);
                     tmem_ld_wait();
+                    uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (gpix * p.out_pitch + n0 + col) * 2;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const int col = c * 32 + g * 8;
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float x = __uint_as_float(v[g * 8 + j]) + sBias[col + j];
+                            const float x = __uint_as_float(v[g * 8 + j]) + sBias[n0 + col + g * 8 + j];
                             f[j] = p.act ? silu_f(x) : x;
                         }
-                        if (res_row && n0 + col < p.N) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(res_row + (n0 + col) * 2);
-                            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                        if (has_res) {
+                            const uint32_t rr[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float2 t = unpack2(rr[j], bf16);
@@ -316,45 +328,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 f[2 * j + 1] += t.y;
                             }
                         }
-                        uint4 o;
-                        o.x = pack2(f[0], f[1], bf16);
-                        o.y = pack2(f[2], f[3], bf16);
-                        o.z = pack2(f[4], f[5], bf16);
-                        o.w = pack2(f[6], f[7], bf16);
-                        const int slab = col / p.out_slab_c;
-                        const uint32_t in_slab = row * slab_row_bytes + (col - slab * p.out_slab_c) * 2;
-                        *reinterpret_cast<uint4*>(sOut + slab * slab_bytes + swz(in_slab, slab_row_bytes)) = o;
+                        if (live && n0 + col + g * 8 < p.N) {
+                            uint4 o;
+                            o.x = pack2(f[0], f[1], bf16);
+                            o.y = pack2(f[2], f[3], bf16);
+                            o.z = pack2(f[4], f[5], bf16);
+                            o.w = pack2(f[6], f[7], bf16);
+                            *reinterpret_cast<uint4*>(op + g * 16) = o;
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator drained: the MMA warp may reuse it
-                fence_proxy_async_smem();                      // generic-proxy smem writes -> visible to the TMA unit
-                named_bar_sync(1, kEpiThreads);
-                if (et == 0) {
-                    const int slabs = BLOCK_N / p.out_slab_c;
-                    for (int s = 0; s < slabs; ++s) {
-                        const int c0 = n0 + s * p.out_slab_c;
-                        if (c0 >= p.N) break;
-                        if (patch) tma_store_4d(&tmO, sOut + s * slab_bytes, c0, ox0, oy0, img);
-                        else tma_store_2d(&tmO, sOut + s * slab_bytes, c0, mt * kBlockM);
-                    }
-                    tma_store_commit();
-                }
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // this warp is done with the accumulator set
             } else {
                 // ---- Detect head (models/yolo.py:95-113): N tile `nt` == anchor; pass 0 raw logits, pass 1 decoded ----
-                uint16_t* stage = reinterpret_cast<uint16_t*>(sOut);   // [128 rows][no]: the exact global layout
+                uint16_t* stage = reinterpret_cast<uint16_t*>(smem + L.off_out);  // [128 rows][no]: the exact global layout
                 const int no = p.no;
                 const int a = nt;
+                const int m0 = ms * kBlockM;
+                const int m = m0 + row;
                 int gx = 0, gy = 0;
-                if (gpix >= 0) { gy = pix / p.nx; gx = pix - gy * p.nx; }
-                const int m0 = mt * kBlockM;
+                if (m < p.M) { const int pix = m % p.HoWo; gy = pix / p.nx; gx = pix - gy * p.nx; }
                 const int rows_here = min(kBlockM, p.M - m0);
                 const int b_lo = m0 / p.HoWo, b_hi = (m0 + rows_here - 1) / p.HoWo;
+                named_bar_sync(1, kEpiThreads);  // previous tile's copy-out finished: the staging block may be rewritten
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
                 for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-                    for (int c = half; c < kHeadN / 32; c += 2) {
-                        if (c * 32 >= no) break;
+                    if (slot * 32 < no) {
+                        const int c = slot;
                         uint32_t v[32];
                         tmem_ld_32x32(t_row + c * 32, v);
                         tmem_ld_wait();
@@ -362,7 +365,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < 32; ++j) {
                             const int o = c * 32 + j;
                             if (o < no) {
-                                float x = __uint_as_float(v[j]) + sBias[o];
+                                float x = __uint_as_float(v[j]) + sBias[n0 + o];
                                 if (pass == 1 && o < 5 + p.nc) {
                                     const float s = sigmoid_f(x);
                                     if (o == 0) x = (s * 2.0f + (static_cast<float>(gx) - 0.5f)) * p.det_stride;
@@ -398,12 +401,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = et; i < n_el; i += kEpiThreads) dst[i] = src[i];
                         }
                     }
-                    named_bar_sync(1, kEpiThreads);
+                    if (pass == 0) named_bar_sync(1, kEpiThreads);
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (EPI == 0 && et == 0) tma_store_wait_all();  // all output bytes committed before the CTA exits
     }
 
     tc_fence_before();
@@ -528,30 +530,34 @@ int encode_im2col(CUtensorMap* map, int dtype, const void* base, int C, int W, i
 }
 
 template <int BN, int EPI>
-cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, int grid, uint32_t smem,
-                        cudaStream_t st) {
+cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, uint32_t smem, cudaStream_t st) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return attr_err;
-    conv_gemm_kernel<BN, EPI><<<grid, kThreads, smem, st>>>(a, b, o, p);
+    conv_gemm_kernel<BN, EPI><<<grid, kThreads, smem, st>>>(a, b, p);
     count_launch();
     return cudaGetLastError();
 }
 
 struct PlanCommon {
-    CUtensorMap tmA, tmB, tmO;
+    CUtensorMap tmA, tmB;
     ConvParams p;
     int block_n, epi, grid;
     uint32_t smem_bytes;
 };
 
-// stage counts from the shared-memory budget; fills p.a_stages/b_stages and pc.smem_bytes/grid
+// stage counts from the shared-memory budget; fills p.a_stages/b_stages and pc.smem_bytes/grid.
+// Expects p.a_sub_bytes, p.b_stage_bytes, p.num_m_tiles set.
 int finish_plan(PlanCommon& pc, int block_n, int epi) {
     ConvParams& p = pc.p;
+    const int mt = mt_for(block_n, epi);
+    p.a_stage_bytes = mt * p.a_sub_bytes;
+    p.num_m_super = (p.num_m_tiles + mt - 1) / mt;
     p.num_n_tiles = epi == 1 ? p.na : (p.N + block_n - 1) / block_n;
+    p.bias_n = p.num_n_tiles * block_n;
     p.idesc = umma_idesc_f16(p.is_bf16 != 0, block_n);
     const uint32_t budget = 225 * 1024 - 1024;
     const bool patch = p.a_mode == A_PATCH;
@@ -559,21 +565,21 @@ int finish_plan(PlanCommon& pc, int block_n, int epi) {
     int a_st = 0, b_st = 0;
     if (!patch) {
         for (int s = kMaxStages; s >= 2; --s)
-            if (smem_layout(block_n, epi, p.no, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
+            if (smem_layout(epi, p.no, p.bias_n, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
         if (a_st > num_kb + 1) a_st = b_st = (num_kb + 1 < 2 ? 2 : num_kb + 1);
     } else {
         for (int a = 3; a >= 2 && !a_st; --a)
             for (int b = kMaxStages; b >= 3; --b)
-                if (smem_layout(block_n, epi, p.no, a, b, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = a; b_st = b; break; }
+                if (smem_layout(epi, p.no, p.bias_n, a, b, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = a; b_st = b; break; }
     }
     if (a_st < 2 || b_st < 2) return set_error(Y5_E_UNSUPPORTED, "conv tile does not fit shared memory (block_n %d a %u b %u)", block_n,
                                                 p.a_stage_bytes, p.b_stage_bytes);
     p.a_stages = a_st;
     p.b_stages = b_st;
-    pc.smem_bytes = smem_layout(block_n, epi, p.no, a_st, b_st, p.a_stage_bytes, p.b_stage_bytes).total + 1024;
+    pc.smem_bytes = smem_layout(epi, p.no, p.bias_n, a_st, b_st, p.a_stage_bytes, p.b_stage_bytes).total + 1024;
     pc.block_n = block_n;
     pc.epi = epi;
-    const long long tiles = static_cast<long long>(p.num_m_tiles) * p.num_n_tiles;
+    const long long tiles = static_cast<long long>(p.num_m_super) * p.num_n_tiles;
     const int sms = sm_count();
     pc.grid = static_cast<int>(tiles < sms ? tiles : sms);
     return 0;
@@ -583,13 +589,13 @@ int run_plan(const PlanCommon& pc, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
     if (pc.epi == 0) {
         switch (pc.block_n) {
-            case 32: e = launch_conv<32, 0>(pc.tmA, pc.tmB, pc.tmO, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 64: e = launch_conv<64, 0>(pc.tmA, pc.tmB, pc.tmO, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 128: e = launch_conv<128, 0>(pc.tmA, pc.tmB, pc.tmO, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 256: e = launch_conv<256, 0>(pc.tmA, pc.tmB, pc.tmO, pc.p, pc.grid, pc.smem_bytes, st); break;
+            case 32: e = launch_conv<32, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+            case 64: e = launch_conv<64, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+            case 128: e = launch_conv<128, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+            case 256: e = launch_conv<256, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
         }
     } else {
-        e = launch_conv<kHeadN, 1>(pc.tmA, pc.tmB, pc.tmO, pc.p, pc.grid, pc.smem_bytes, st);
+        e = launch_conv<kHeadN, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st);
     }
     if (e != cudaSuccess) return set_error(int(e), "conv_gemm launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -675,13 +681,14 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     p.is_bf16 = d->dtype == Y5_BF16;
     p.act = d->act;
     p.bias = d->bias;
+    p.out = d->out;
+    p.out_pitch = d->out_pitch;
     p.res = d->residual;
     p.res_pitch = d->res_pitch;
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
     const int row_bytes = bk * 2;
     p.b_stage_bytes = bn * row_bytes;
-    p.out_slab_c = bn >= 64 ? 64 : 32;
     const bool plain = g.kh == 1 && g.kw == 1 && d->stride == 1 && g.pad_h == 0 && g.pad_w == 0 && !d->in_x_stride && !d->in_y_stride &&
                        !d->in_n_stride;
     // spatial tile for PATCH mode: th x tw = 128 with tw in {8..128}; pick the shape wasting the fewest pixels
@@ -700,18 +707,17 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     else p.a_mode = A_IM2COL;
 
     const CUtensorMapSwizzle sw = swizzle_for_row_bytes(row_bytes);
-    const CUtensorMapSwizzle sw_out = swizzle_for_row_bytes(p.out_slab_c * 2);
     int e = 0;
     if (p.a_mode == A_LINEAR) {
         p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
-        p.a_stage_bytes = kBlockM * row_bytes;
+        p.a_sub_bytes = kBlockM * row_bytes;
         cuuint64_t dims[2] = {(cuuint64_t)d->in_c, (cuuint64_t)p.M};
         cuuint64_t str[1] = {(cuuint64_t)d->in_pitch * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, kBlockM};
         e = encode_tiled(&pc.tmA, d->dtype, d->in, 2, dims, str, box, sw, "A linear");
     } else if (p.a_mode == A_IM2COL) {
         p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
-        p.a_stage_bytes = kBlockM * row_bytes;
+        p.a_sub_bytes = kBlockM * row_bytes;
         e = encode_im2col(&pc.tmA, d->dtype, d->in, d->in_c, d->in_w, d->in_h, d->batch, g.xs, g.ys, g.ns, g.kh, g.kw, d->stride, g.pad_h,
                           g.pad_w, bk, kBlockM, sw);
     } else {
@@ -720,7 +726,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         p.tiles_x = (g.Wo + p.tw - 1) / p.tw;
         p.tiles_y = (g.Ho + p.th - 1) / p.th;
         p.num_m_tiles = d->batch * p.tiles_x * p.tiles_y;
-        p.a_stage_bytes = (p.th + g.kh - 1) * p.tw * row_bytes;
+        p.a_sub_bytes = (p.th + g.kh - 1) * p.tw * row_bytes;
         cuuint64_t dims[4] = {(cuuint64_t)d->in_c, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->batch};
         cuuint64_t str[3] = {(cuuint64_t)g.xs * 2, (cuuint64_t)g.ys * 2, (cuuint64_t)g.ns * 2};
         cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)(p.th + g.kh - 1), 1};
@@ -733,18 +739,6 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         cuuint64_t str[1] = {ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
         e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, dims, str, box, sw, "B");
-    }
-    if (e) { delete plan; return e; }
-    if (p.a_mode == A_PATCH) {
-        cuuint64_t dims[4] = {(cuuint64_t)d->out_c, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d->batch};
-        cuuint64_t str[3] = {(cuuint64_t)d->out_pitch * 2, (cuuint64_t)g.Wo * d->out_pitch * 2, (cuuint64_t)g.Ho * g.Wo * d->out_pitch * 2};
-        cuuint32_t box[4] = {(cuuint32_t)p.out_slab_c, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
-        e = encode_tiled(&pc.tmO, d->dtype, d->out, 4, dims, str, box, sw_out, "out spatial");
-    } else {
-        cuuint64_t dims[2] = {(cuuint64_t)d->out_c, (cuuint64_t)p.M};
-        cuuint64_t str[1] = {(cuuint64_t)d->out_pitch * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.out_slab_c, kBlockM};
-        e = encode_tiled(&pc.tmO, d->dtype, d->out, 2, dims, str, box, sw_out, "out linear");
     }
     if (e) { delete plan; return e; }
     if (int e2 = finish_plan(pc, bn, 0)) { delete plan; return e2; }
@@ -817,7 +811,7 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
     const int row_bytes = bk * 2;
-    p.a_stage_bytes = kBlockM * row_bytes;
+    p.a_sub_bytes = kBlockM * row_bytes;
     p.b_stage_bytes = kHeadN * row_bytes;
     p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
     const CUtensorMapSwizzle sw = swizzle_for_row_bytes(row_bytes);
@@ -832,7 +826,6 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     cuuint32_t bbox[2] = {(cuuint32_t)bk, (cuuint32_t)kHeadN};
     e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, bdims, bstr, bbox, sw, "head B");
     if (e) { delete plan; return e; }
-    pc.tmO = pc.tmB;  // unused by the head epilogue
     if (int e2 = finish_plan(pc, kHeadN, 1)) { delete plan; return e2; }
     *out = plan;
     return 0;
