@@ -61,6 +61,15 @@ def test_conv_every_tile_width(cuda, bn):
     assert rel_err(got, ref) < 2e-3
 
 
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("case,a_mode", [((2, 20, 20, 64, 256, 3, 1, 1), 1), ((2, 20, 20, 64, 256, 3, 1, 1), 2),
+                                         ((3, 16, 16, 128, 256, 1, 1, 0), 0), ((1, 40, 40, 128, 384, 3, 2, 1), 0)])
+def test_conv_256_row_tiles(cuda, bn, case, a_mode):
+    """MT = 2: two 128-row sub-tiles share every B tile (256x128 double-buffered, 256x256 single-buffered accumulators)."""
+    got, ref, _ = conv_case(cuda, torch.float16, *case, block_n=bn, mt2=True, a_mode=a_mode, residual=True)
+    assert rel_err(got, ref) < 2e-3, (bn, case, a_mode, rel_err(got, ref))
+
+
 def test_tensor_core_path_agrees_with_direct_kernel(cuda):
     """Two independent device implementations of the same op (tcgen05 GEMM vs CUDA-core direct conv)."""
     a, ref, _ = conv_case(cuda, torch.float16, 2, 20, 20, 64, 64, 3, 1, 1, seed=5)

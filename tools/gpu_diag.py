@@ -73,6 +73,11 @@ def s3_epilogue_variants():
     for bn in (32, 64, 128, 256):
         _conv(f"block_n {bn}", 2, 20, 20, 64, 256, 3, 1, 1, block_n=bn)
     _conv("many tiles", 8, 80, 80, 64, 64, 3, 1, 1)
+    for bn in (128, 256):
+        _conv(f"MT=2 block_n {bn} im2col", 2, 20, 20, 64, 256, 3, 1, 1, block_n=bn, mt2=True, a_mode=1, residual=True)
+        _conv(f"MT=2 block_n {bn} patch", 2, 20, 20, 64, 256, 3, 1, 1, block_n=bn, mt2=True, a_mode=2, residual=True)
+        _conv(f"MT=2 block_n {bn} 1x1", 3, 16, 16, 128, 256, 1, 1, 0, block_n=bn, mt2=True)
+        _conv(f"MT=2 block_n {bn} s2 N=384", 1, 40, 40, 128, 384, 3, 2, 1, block_n=bn, mt2=True)
 
 
 @stage

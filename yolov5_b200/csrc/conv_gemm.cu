@@ -51,6 +51,8 @@ enum AMode { A_LINEAR = 0, A_IM2COL = 1, A_PATCH = 2 };
 // latencies (barrier round trips, TMEM load, first global access) are amortised over the same amount of output whatever
 // the channel count, and one B tile feeds MT sub-tiles.
 __host__ __device__ constexpr int mt_for(int block_n, int epi) { return (epi == 0 && block_n < 128) ? 128 / block_n : 1; }
+// For BLOCK_N >= 128 the host may also pick MT = 2 (tiles of 256 x 128 / 256 x 256): deep-K layers are bound by
+// L2->smem operand traffic, and a 256x256 tile needs half the bytes per flop of a 128x128 one.
 
 struct ConvParams {
     int M, N;                   // GEMM rows (B*Ho*Wo), output channels
@@ -106,13 +108,13 @@ __host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, i
     return L;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-    constexpr int MT = mt_for(BLOCK_N, EPI);
-    constexpr int kAccCols = MT * BLOCK_N;          // TMEM columns per accumulator set (128 or 256)
-    constexpr uint32_t kTmemCols = 2 * kAccCols;    // two sets: epilogue of tile i overlaps the MMAs of tile i+1
-    constexpr int kChunks = kAccCols / 32;          // 32-column epilogue work items per tile (4 or 8)
+    constexpr int kAccCols = MT * BLOCK_N;          // TMEM columns per accumulator set (128, 256 or 512)
+    constexpr int NACC = kAccCols <= 256 ? 2 : 1;   // two sets when they fit: epilogue of tile i overlaps the MMAs of tile i+1
+    constexpr uint32_t kTmemCols = NACC * kAccCols < 32 ? 32 : NACC * kAccCols;
+    constexpr int kChunks = kAccCols / 32;          // 32-column epilogue work items per tile (4, 8 or 16)
     constexpr int kChunksPerSub = BLOCK_N / 32;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -255,7 +257,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -404,7 +406,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (pass == 0) named_bar_sync(1, kEpiThreads);
                 }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -477,10 +479,33 @@ int pick_block_n(int out_c, int64_t m_rows) {
     if (out_c <= 64) return 64;
     if (out_c <= 128) return 128;
     const int64_t m_tiles = (m_rows + kBlockM - 1) / kBlockM;
-    // prefer 256-wide tiles (half the A re-reads and B-operand smem traffic per flop) when that still leaves >= 2 waves
     const int64_t tiles256 = m_tiles * ((out_c + 255) / 256);
     if (tiles256 >= 2 * 148 && (out_c % 256 == 0 || out_c > 384)) return 256;
     return 128;
+}
+
+// Tile shape (block_n, mt) for out_c > 64 from a three-term model: operand bytes over the measured L2->SM rate,
+// tensor-pipe cycles (N/2 per M128xNxK16 instruction) with wave quantisation over the SMs, and a fixed cost per tile.
+void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_bytes_per_sub_kb, int* block_n, int* mt) {
+    if (out_c <= 32) { *block_n = 32; *mt = 4; return; }
+    if (out_c <= 64) { *block_n = 64; *mt = 2; return; }
+    const double l2_bytes_per_cycle = 3300.0;  // chip-wide, sustained (B200 measured ~6.3 TB/s at 1.9 GHz)
+    const int sms = 148;
+    const int64_t m_tiles = (m_rows + kBlockM - 1) / kBlockM;
+    double best = 1e30;
+    for (int bn : {128, 256}) {
+        if (bn == 256 && out_c <= 128) continue;
+        for (int m : {1, 2}) {
+            const int64_t tiles = ((m_tiles + m - 1) / m) * ((out_c + bn - 1) / bn);
+            const int64_t waves = (tiles + sms - 1) / sms;
+            const double bytes_per_kb = m * a_bytes_per_sub_kb + bn * block_k * 2.0;
+            const double t_l2 = tiles * (double)num_kb * bytes_per_kb / l2_bytes_per_cycle;
+            const double t_mma = waves * (double)num_kb * (block_k / 16) * m * (bn / 2.0);
+            const double t_fix = waves * (2500.0 + (m * bn == 512 ? 3000.0 : 0.0));  // single-buffered accumulators expose the epilogue
+            const double t = (t_l2 > t_mma ? t_l2 : t_mma) + t_fix;
+            if (t < best) { best = t; *block_n = bn; *mt = m; }
+        }
+    }
 }
 
 CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
@@ -529,15 +554,15 @@ int encode_im2col(CUtensorMap* map, int dtype, const void* base, int C, int W, i
     return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, uint32_t smem, cudaStream_t st) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return attr_err;
-    conv_gemm_kernel<BN, EPI><<<grid, kThreads, smem, st>>>(a, b, p);
+    conv_gemm_kernel<BN, EPI, MT><<<grid, kThreads, smem, st>>>(a, b, p);
     count_launch();
     return cudaGetLastError();
 }
@@ -545,15 +570,14 @@ cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvPa
 struct PlanCommon {
     CUtensorMap tmA, tmB;
     ConvParams p;
-    int block_n, epi, grid;
+    int block_n, epi, mt, grid;
     uint32_t smem_bytes;
 };
 
 // stage counts from the shared-memory budget; fills p.a_stages/b_stages and pc.smem_bytes/grid.
 // Expects p.a_sub_bytes, p.b_stage_bytes, p.num_m_tiles set.
-int finish_plan(PlanCommon& pc, int block_n, int epi) {
+int finish_plan(PlanCommon& pc, int block_n, int epi, int mt) {
     ConvParams& p = pc.p;
-    const int mt = mt_for(block_n, epi);
     p.a_stage_bytes = mt * p.a_sub_bytes;
     p.num_m_super = (p.num_m_tiles + mt - 1) / mt;
     p.num_n_tiles = epi == 1 ? p.na : (p.N + block_n - 1) / block_n;
@@ -579,6 +603,7 @@ int finish_plan(PlanCommon& pc, int block_n, int epi) {
     pc.smem_bytes = smem_layout(epi, p.no, p.bias_n, a_st, b_st, p.a_stage_bytes, p.b_stage_bytes).total + 1024;
     pc.block_n = block_n;
     pc.epi = epi;
+    pc.mt = mt;
     const long long tiles = static_cast<long long>(p.num_m_super) * p.num_n_tiles;
     const int sms = sm_count();
     pc.grid = static_cast<int>(tiles < sms ? tiles : sms);
@@ -587,15 +612,16 @@ int finish_plan(PlanCommon& pc, int block_n, int epi) {
 
 int run_plan(const PlanCommon& pc, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
-    if (pc.epi == 0) {
-        switch (pc.block_n) {
-            case 32: e = launch_conv<32, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 64: e = launch_conv<64, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 128: e = launch_conv<128, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-            case 256: e = launch_conv<256, 0>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        }
-    } else {
-        e = launch_conv<kHeadN, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st);
+    const int key = pc.epi * 10000 + pc.block_n * 10 + pc.mt;
+    switch (key) {
+        case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 1282: e = launch_conv<128, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 2561: e = launch_conv<256, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 2562: e = launch_conv<256, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 11281: e = launch_conv<kHeadN, 1, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        default: return set_error(Y5_E_UNSUPPORTED, "conv: no kernel for block_n %d mt %d epi %d", pc.block_n, pc.mt, pc.epi);
     }
     if (e != cudaSuccess) return set_error(int(e), "conv_gemm launch failed: %s", cudaGetErrorString(e));
     return 0;
@@ -665,8 +691,16 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     const int64_t M64 = static_cast<int64_t>(d->batch) * g.Ho * g.Wo;
     if (M64 > 0x7fffffff - 256) return set_error(Y5_E_UNSUPPORTED, "conv: more than 2^31 output pixels");
     const int bk = d->block_k ? d->block_k : pick_block_k(d->in_c);
-    const int bn = d->block_n ? d->block_n : pick_block_n(d->out_c, M64);
+    int bn = d->block_n, mt_sel = 0;
     if (bk != 16 && bk != 32 && bk != 64) return set_error(Y5_E_INVALID, "conv: block_k must be 16/32/64");
+    {
+        const int kw_ = d->kw ? d->kw : d->ksize;
+        const int num_kb = d->ksize * kw_ * ((d->in_c + bk - 1) / bk);
+        int bn_auto = 0;
+        pick_tile(d->out_c, M64, num_kb, bk, 128.0 * bk * 2.0, &bn_auto, &mt_sel);
+        if (!bn) bn = bn_auto;
+        else mt_sel = bn < 128 ? 128 / bn : (d->reserved == 2 ? 2 : 1);  // forced block_n (tests): reserved = 2 asks for MT = 2
+    }
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
     auto* plan = new y5_conv_plan();
     PlanCommon& pc = plan->pc;
@@ -741,7 +775,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, dims, str, box, sw, "B");
     }
     if (e) { delete plan; return e; }
-    if (int e2 = finish_plan(pc, bn, 0)) { delete plan; return e2; }
+    if (int e2 = finish_plan(pc, bn, 0, mt_sel)) { delete plan; return e2; }
     *out = plan;
     return 0;
 }
@@ -826,7 +860,7 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     cuuint32_t bbox[2] = {(cuuint32_t)bk, (cuuint32_t)kHeadN};
     e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, bdims, bstr, bbox, sw, "head B");
     if (e) { delete plan; return e; }
-    if (int e2 = finish_plan(pc, kHeadN, 1)) { delete plan; return e2; }
+    if (int e2 = finish_plan(pc, kHeadN, 1, 1)) { delete plan; return e2; }
     *out = plan;
     return 0;
 }

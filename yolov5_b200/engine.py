@@ -152,9 +152,7 @@ class Program:
         m_rows = self.B * ho * wo
         bk, bn = C.c_int32(), C.c_int32()
         _lib.check(self.lib.y5_conv_pick(cin, cout, m_rows, C.byref(bk), C.byref(bn)), "conv_pick")
-        bn_env = os.environ.get("Y5_FORCE_BLOCK_N")
-        if bn_env:
-            bn.value = int(bn_env)
+        bn.value = int(os.environ.get("Y5_FORCE_BLOCK_N", "0"))  # 0: the library's tile cost model decides (block_n, MT)
         wp = pack_weight(w_fp32, bk.value, self.dtype)
         bias = b_fp32.to(torch.float32).contiguous()
         self._keep += [wp, bias]
