@@ -81,7 +81,8 @@ typedef struct y5_conv_desc {
     int64_t in_y_stride;  /* elements between rows   (0 = in_w * in_x_stride) */
     int64_t in_n_stride;  /* elements between images (0 = in_h * in_y_stride) */
     int32_t a_mode;       /* activation fetch: 0 auto, 1 force TMA-im2col, 2 force shifted-patch (stride-1 only) */
-    int32_t reserved;     /* with a forced block_n >= 128: 2 = use 256-row tiles (two 128-row sub-tiles per B tile); else 0 */
+    int32_t reserved;     /* tuning/tests, only read with a forced block_n >= 128: bit 1 = 256-row tiles (two 128-row
+                             sub-tiles per B tile); bits 8.. = thread-block cluster size (2|4) for weight-tile multicast */
 } y5_conv_desc;
 
 /* Tiling the library will use for a conv: block_k decides the weight packing (cin_pad = ceil(in_c/block_k)*block_k). */

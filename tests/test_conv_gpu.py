@@ -70,6 +70,16 @@ def test_conv_256_row_tiles(cuda, bn, case, a_mode):
     assert rel_err(got, ref) < 2e-3, (bn, case, a_mode, rel_err(got, ref))
 
 
+@pytest.mark.parametrize("bn,mt2", [(128, False), (128, True), (256, False), (256, True)])
+@pytest.mark.parametrize("case,a_mode", [((4, 40, 40, 64, 256, 3, 1, 1), 2), ((4, 40, 40, 64, 256, 3, 1, 1), 1), ((5, 24, 24, 128, 512, 1, 1, 0), 0),
+                                         ((3, 40, 40, 128, 384, 3, 2, 1), 0)])
+def test_conv_cluster_multicast(cuda, bn, mt2, case, a_mode):
+    """2-CTA clusters: each CTA fetches half of every weight tile and TMA-multicasts it to its peer; odd super-tile
+    counts leave one CTA of the last cluster without work (it must still take part in the multicast protocol)."""
+    got, ref, _ = conv_case(cuda, torch.float16, *case, block_n=bn, mt2=mt2, cluster=2, a_mode=a_mode, residual=True)
+    assert rel_err(got, ref) < 2e-3, (bn, mt2, case, a_mode, rel_err(got, ref))
+
+
 def test_tensor_core_path_agrees_with_direct_kernel(cuda):
     """Two independent device implementations of the same op (tcgen05 GEMM vs CUDA-core direct conv)."""
     a, ref, _ = conv_case(cuda, torch.float16, 2, 20, 20, 64, 64, 3, 1, 1, seed=5)

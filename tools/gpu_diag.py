@@ -81,6 +81,14 @@ def s3_epilogue_variants():
 
 
 @stage
+def s3b_cluster():
+    for bn, mt2 in ((128, False), (128, True), (256, False), (256, True)):
+        _conv(f"cluster2 bn{bn} mt2={mt2} patch", 4, 40, 40, 64, 256, 3, 1, 1, block_n=bn, mt2=mt2, cluster=2, a_mode=2, residual=True)
+        _conv(f"cluster2 bn{bn} mt2={mt2} 1x1 odd", 5, 24, 24, 128, 512, 1, 1, 0, block_n=bn, mt2=mt2, cluster=2)
+        _conv(f"cluster2 bn{bn} mt2={mt2} s2", 3, 40, 40, 128, 384, 3, 2, 1, block_n=bn, mt2=mt2, cluster=2)
+
+
+@stage
 def s4_model():
     import numpy as np
     import torch

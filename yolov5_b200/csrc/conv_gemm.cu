@@ -29,6 +29,7 @@
 // Replaces reference models/common.py:86-92 (Conv), :181 (Bottleneck add), :246/:340/:453 (cat, via strided
 // output views) and models/yolo.py:95-113 (Detect level).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -133,6 +134,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // Thread-block cluster (1 or 2+ CTAs along M): the CTAs of a cluster work on different M super-tiles of the SAME
+    // N tile in lock-step over K, each fetches 1/csize of every weight tile and TMA-multicasts it to all of them.
+    const uint32_t csize = cluster_nctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -141,7 +147,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
+            mbar_init(&b_empty[s], csize);  // released by the MMA thread of every CTA in the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
@@ -154,10 +160,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) sBias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = p.num_m_super * p.num_n_tiles;
+    // tiles are (group of csize M super-tiles, N tile); this CTA takes super-tile group*csize + crank
+    const int num_tiles = ((p.num_m_super + static_cast<int>(csize) - 1) / static_cast<int>(csize)) * p.num_n_tiles;
+    const int tile0 = blockIdx.x / csize, tile_step = gridDim.x / csize;
     const uint32_t row_bytes = p.block_k * 2;
     const bool patch = p.a_mode == A_PATCH;
     // K iteration: "A groups" each feeding `grp` consecutive B tiles.
@@ -171,8 +180,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int ms = tile / p.num_n_tiles;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int ms = (tile / p.num_n_tiles) * csize + crank;
                 const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
                 int img[MT], y0[MT], x0[MT];  // IM2COL: base pixel of the first window; PATCH: sub-tile origin
 #pragma unroll
@@ -216,7 +225,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int kb = (r * p.kw + s) * p.c_chunks + cc;
                         mbar_wait(&b_empty[bs], bph ^ 1);
                         mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
-                        tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
+                        if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
+                        else {  // my slice of the rows, delivered to every CTA of the cluster
+                            const uint32_t slice_rows = BLOCK_N / csize;
+                            tma_load_2d_mcast(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes + crank * slice_rows * row_bytes, kb * p.block_k,
+                                              n0 + crank * slice_rows, cmask);
+                        }
                         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
                     }
                 }
@@ -229,7 +243,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t aph = 0, bph = 0, acc_phase = 0;
             const int k_steps = p.block_k / 16;
             const uint32_t a_shift = patch ? p.tw * row_bytes : 0;  // smem bytes between vertical taps inside a patch
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccCols;
@@ -250,7 +264,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                             accum = 1;
                         }
-                        umma_commit(&b_empty[bs]);
+                        if (csize == 1) umma_commit(&b_empty[bs]);
+                        else umma_commit_mcast(&b_empty[bs], cmask);
                         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
                     }
                     umma_commit(&a_empty[as]);
@@ -273,8 +288,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool bf16 = p.is_bf16 != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int ms = tile / p.num_n_tiles;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            const int ms = (tile / p.num_n_tiles) * csize + crank;
             const int nt = tile % p.num_n_tiles;
             const int n0 = nt * BLOCK_N;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
@@ -412,6 +427,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -486,7 +502,8 @@ int pick_block_n(int out_c, int64_t m_rows) {
 
 // Tile shape (block_n, mt) for out_c > 64 from a three-term model: operand bytes over the measured L2->SM rate,
 // tensor-pipe cycles (N/2 per M128xNxK16 instruction) with wave quantisation over the SMs, and a fixed cost per tile.
-void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_bytes_per_sub_kb, int* block_n, int* mt) {
+void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_bytes_per_sub_kb, int* block_n, int* mt, int* cluster) {
+    *cluster = 1;
     if (out_c <= 32) { *block_n = 32; *mt = 4; return; }
     if (out_c <= 64) { *block_n = 64; *mt = 2; return; }
     const double l2_bytes_per_cycle = 3300.0;  // chip-wide, sustained (B200 measured ~6.3 TB/s at 1.9 GHz)
@@ -496,14 +513,18 @@ void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_byte
     for (int bn : {128, 256}) {
         if (bn == 256 && out_c <= 128) continue;
         for (int m : {1, 2}) {
-            const int64_t tiles = ((m_tiles + m - 1) / m) * ((out_c + bn - 1) / bn);
-            const int64_t waves = (tiles + sms - 1) / sms;
-            const double bytes_per_kb = m * a_bytes_per_sub_kb + bn * block_k * 2.0;
-            const double t_l2 = tiles * (double)num_kb * bytes_per_kb / l2_bytes_per_cycle;
-            const double t_mma = waves * (double)num_kb * (block_k / 16) * m * (bn / 2.0);
-            const double t_fix = waves * (2500.0 + (m * bn == 512 ? 3000.0 : 0.0));  // single-buffered accumulators expose the epilogue
-            const double t = (t_l2 > t_mma ? t_l2 : t_mma) + t_fix;
-            if (t < best) { best = t; *block_n = bn; *mt = m; }
+            for (int cl : {1, 2}) {
+                const int64_t m_super = (m_tiles + m - 1) / m;
+                if (cl > 1 && m_super < 2 * cl) continue;
+                const int64_t tiles = ((m_super + cl - 1) / cl) * cl * ((out_c + bn - 1) / bn);  // CTA-tiles incl. cluster padding
+                const int64_t waves = (tiles + sms - 1) / sms;
+                const double bytes_per_kb = m * a_bytes_per_sub_kb + bn * block_k * 2.0 / cl;  // multicast: each CTA pulls 1/cl of B from L2
+                const double t_l2 = tiles * (double)num_kb * bytes_per_kb / l2_bytes_per_cycle;
+                const double t_mma = waves * (double)num_kb * (block_k / 16) * m * (bn / 2.0);
+                const double t_fix = waves * (2500.0 + (m * bn == 512 ? 3000.0 : 0.0)) + (cl > 1 ? 1500.0 : 0.0);
+                const double t = (t_l2 > t_mma ? t_l2 : t_mma) + t_fix;
+                if (t < best) { best = t; *block_n = bn; *mt = m; *cluster = cl; }
+            }
         }
     }
 }
@@ -555,28 +576,43 @@ int encode_im2col(CUtensorMap* map, int dtype, const void* base, int C, int W, i
 }
 
 template <int BN, int EPI, int MT>
-cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, uint32_t smem, cudaStream_t st) {
+cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, int cluster, uint32_t smem, cudaStream_t st) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return attr_err;
-    conv_gemm_kernel<BN, EPI, MT><<<grid, kThreads, smem, st>>>(a, b, p);
     count_launch();
-    return cudaGetLastError();
+    if (cluster <= 1) {
+        conv_gemm_kernel<BN, EPI, MT><<<grid, kThreads, smem, st>>>(a, b, p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, MT>, a, b, p);
 }
 
 struct PlanCommon {
     CUtensorMap tmA, tmB;
     ConvParams p;
-    int block_n, epi, mt, grid;
+    int block_n, epi, mt, grid, cluster;
     uint32_t smem_bytes;
 };
 
 // stage counts from the shared-memory budget; fills p.a_stages/b_stages and pc.smem_bytes/grid.
 // Expects p.a_sub_bytes, p.b_stage_bytes, p.num_m_tiles set.
-int finish_plan(PlanCommon& pc, int block_n, int epi, int mt) {
+int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1) {
     ConvParams& p = pc.p;
     p.a_stage_bytes = mt * p.a_sub_bytes;
     p.num_m_super = (p.num_m_tiles + mt - 1) / mt;
@@ -604,9 +640,10 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt) {
     pc.block_n = block_n;
     pc.epi = epi;
     pc.mt = mt;
-    const long long tiles = static_cast<long long>(p.num_m_super) * p.num_n_tiles;
-    const int sms = sm_count();
-    pc.grid = static_cast<int>(tiles < sms ? tiles : sms);
+    pc.cluster = cluster;
+    const long long tiles = static_cast<long long>((p.num_m_super + cluster - 1) / cluster) * p.num_n_tiles;  // per cluster
+    const int max_clusters = sm_count() / cluster;  // 1 CTA per SM (shared memory); pairs pack perfectly on 148 SMs
+    pc.grid = static_cast<int>(tiles < max_clusters ? tiles : max_clusters) * cluster;
     return 0;
 }
 
@@ -614,13 +651,13 @@ int run_plan(const PlanCommon& pc, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
     const int key = pc.epi * 10000 + pc.block_n * 10 + pc.mt;
     switch (key) {
-        case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 1282: e = launch_conv<128, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 2561: e = launch_conv<256, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 2562: e = launch_conv<256, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
-        case 11281: e = launch_conv<kHeadN, 1, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.smem_bytes, st); break;
+        case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 1282: e = launch_conv<128, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 2561: e = launch_conv<256, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 2562: e = launch_conv<256, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 11281: e = launch_conv<kHeadN, 1, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, 1, pc.smem_bytes, st); break;
         default: return set_error(Y5_E_UNSUPPORTED, "conv: no kernel for block_n %d mt %d epi %d", pc.block_n, pc.mt, pc.epi);
     }
     if (e != cudaSuccess) return set_error(int(e), "conv_gemm launch failed: %s", cudaGetErrorString(e));
@@ -691,15 +728,20 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     const int64_t M64 = static_cast<int64_t>(d->batch) * g.Ho * g.Wo;
     if (M64 > 0x7fffffff - 256) return set_error(Y5_E_UNSUPPORTED, "conv: more than 2^31 output pixels");
     const int bk = d->block_k ? d->block_k : pick_block_k(d->in_c);
-    int bn = d->block_n, mt_sel = 0;
+    int bn = d->block_n, mt_sel = 0, cl_sel = 1;
     if (bk != 16 && bk != 32 && bk != 64) return set_error(Y5_E_INVALID, "conv: block_k must be 16/32/64");
     {
         const int kw_ = d->kw ? d->kw : d->ksize;
         const int num_kb = d->ksize * kw_ * ((d->in_c + bk - 1) / bk);
         int bn_auto = 0;
-        pick_tile(d->out_c, M64, num_kb, bk, 128.0 * bk * 2.0, &bn_auto, &mt_sel);
+        pick_tile(d->out_c, M64, num_kb, bk, 128.0 * bk * 2.0, &bn_auto, &mt_sel, &cl_sel);
         if (!bn) bn = bn_auto;
-        else mt_sel = bn < 128 ? 128 / bn : (d->reserved == 2 ? 2 : 1);  // forced block_n (tests): reserved = 2 asks for MT = 2
+        else {  // forced block_n (tests / tuning): reserved bit 1 asks for MT = 2, bits 8.. give the cluster size
+            mt_sel = bn < 128 ? 128 / bn : ((d->reserved & 2) ? 2 : 1);
+            cl_sel = (d->reserved >> 8) > 1 ? (d->reserved >> 8) : 1;
+        }
+        if (const char* e = getenv("Y5_CLUSTER")) cl_sel = atoi(e) > 1 && bn >= 128 ? atoi(e) : 1;
+        if (cl_sel != 1 && cl_sel != 2 && cl_sel != 4) cl_sel = 1;
     }
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
     auto* plan = new y5_conv_plan();
@@ -771,11 +813,11 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     {
         cuuint64_t dims[2] = {ktot, (cuuint64_t)d->out_c};
         cuuint64_t str[1] = {ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)(bn / cl_sel)};
         e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, dims, str, box, sw, "B");
     }
     if (e) { delete plan; return e; }
-    if (int e2 = finish_plan(pc, bn, 0, mt_sel)) { delete plan; return e2; }
+    if (int e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel)) { delete plan; return e2; }
     *out = plan;
     return 0;
 }
