@@ -513,7 +513,7 @@ void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_byte
     for (int bn : {128, 256}) {
         if (bn == 256 && out_c <= 128) continue;
         for (int m : {1, 2}) {
-            for (int cl : {1, 2}) {
+            for (int cl : {1}) {  // {1, 2}: weight-tile multicast measured no faster on B200 (L2 dedups concurrent reads); kept selectable
                 const int64_t m_super = (m_tiles + m - 1) / m;
                 if (cl > 1 && m_super < 2 * cl) continue;
                 const int64_t tiles = ((m_super + cl - 1) / cl) * cl * ((out_c + bn - 1) / bn);  // CTA-tiles incl. cluster padding
