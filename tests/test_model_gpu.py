@@ -127,6 +127,13 @@ def test_model_yolov5l_bs2(cuda):
     _check_model("yolov5l", (2, 3, 320, 320), 4, 104, torch.float16, cuda)
 
 
+@pytest.mark.parametrize("name,shape", [("yolov5m", (2, 3, 128, 160)), ("yolov5x-seg", (1, 3, 128, 128)), ("yolov5x", (1, 3, 96, 96))])
+def test_model_widths_not_multiple_of_16(cuda, name, shape):
+    """yolov5m / yolov5x channel counts (48, 96, 192 / 80, 160, 320 ...) are not multiples of the 64-channel K block:
+    the K tail is zero-filled by TMA (out-of-bounds box) and the weights are zero padded.  x-seg adds Proto + no=117."""
+    _check_model(name, shape, 7, 107, torch.float16, cuda)
+
+
 def test_uint8_input_and_graph_replay_is_deterministic(cuda):
     m = DetectionModel("yolov5n")
     m.load_state_dict(model_ref.synth_state_dict(model_cfg("yolov5n"), seed=5))
