@@ -97,7 +97,7 @@ __host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, i
     o += b_stages * b_bytes;
     o = (o + 1023) & ~1023u;
     L.off_out = o;
-    if (epi == 1) o += (kBlockM * no * 2 + 1023) & ~1023u;  // head: one anchor's [128][no] block in its global layout
+    if (epi == 1) o += 4 * ((kBlockM * no * 2 + 1023) & ~1023u);  // head: 2 sets x {raw, decoded} blocks [128][no], global layout
     L.off_bias = o;
     o += ((bias_n + 3) & ~3) * 4;
     o = (o + 7) & ~7u;
@@ -177,7 +177,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        {   // the whole warp runs the loop with warp-uniform state; one elected lane issues the copies (keeps the TMA
+            // operands in uniform registers: a divergent `lane == 0` region makes the compiler wrap every UTMALDG in a
+            // vote / elect / R2UR waterfall)
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -204,45 +206,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         x0[mi] = (rem - ty * p.tiles_x) * p.tw - p.pad_w;
                     }
                 }
-                for (int g = 0; g < num_groups; ++g) {
-                    int cc, s, r0;
-                    if (patch) { cc = g / p.kw; s = g - cc * p.kw; r0 = 0; }
-                    else { const int t = g / p.c_chunks; cc = g - t * p.c_chunks; r0 = t / p.kw; s = t - r0 * p.kw; }
+                // one A group + its B tiles; PATCH walks (cc, s){r}, the other modes walk (r, s, cc)
+                auto issue_group = [&](int cc, int s, int r0) {
                     mbar_wait(&a_empty[as], aph ^ 1);
-                    mbar_arrive_expect_tx(&a_full[as], p.a_stage_bytes);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&a_full[as], p.a_stage_bytes);
 #pragma unroll
-                    for (int mi = 0; mi < MT; ++mi) {
-                        uint8_t* a_dst = sA + as * p.a_stage_bytes + mi * p.a_sub_bytes;
-                        if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
-                        else if (p.a_mode == A_IM2COL)
-                            tma_load_im2col_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
-                                               static_cast<uint16_t>(s), static_cast<uint16_t>(r0));
-                        else tma_load_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi] + s, y0[mi], img[mi]);
+                        for (int mi = 0; mi < MT; ++mi) {
+                            uint8_t* a_dst = sA + as * p.a_stage_bytes + mi * p.a_sub_bytes;
+                            if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
+                            else if (p.a_mode == A_IM2COL)
+                                tma_load_im2col_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
+                                                   static_cast<uint16_t>(s), static_cast<uint16_t>(r0));
+                            else tma_load_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi] + s, y0[mi], img[mi]);
+                        }
                     }
+                    __syncwarp();
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                     for (int j = 0; j < grp; ++j) {
                         const int r = patch ? j : r0;
                         const int kb = (r * p.kw + s) * p.c_chunks + cc;
                         mbar_wait(&b_empty[bs], bph ^ 1);
-                        mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
-                        if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
-                        else {  // my slice of the rows, delivered to every CTA of the cluster
-                            const uint32_t slice_rows = BLOCK_N / csize;
-                            tma_load_2d_mcast(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes + crank * slice_rows * row_bytes, kb * p.block_k,
-                                              n0 + crank * slice_rows, cmask);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
+                            if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
+                            else {  // my slice of the rows, delivered to every CTA of the cluster
+                                const uint32_t slice_rows = BLOCK_N / csize;
+                                tma_load_2d_mcast(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes + crank * slice_rows * row_bytes,
+                                                  kb * p.block_k, n0 + crank * slice_rows, cmask);
+                            }
                         }
+                        __syncwarp();
                         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
                     }
+                };
+                if (patch) {
+                    for (int cc = 0; cc < p.c_chunks; ++cc)
+                        for (int s = 0; s < p.kw; ++s) issue_group(cc, s, 0);
+                } else {
+                    for (int r = 0; r < p.kh; ++r)
+                        for (int s = 0; s < p.kw; ++s)
+                            for (int cc = 0; cc < p.c_chunks; ++cc) issue_group(cc, s, r);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
+        {   // whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase = 0;
             const int k_steps = p.block_k / 16;
-            const uint32_t a_shift = patch ? p.tw * row_bytes : 0;  // smem bytes between vertical taps inside a patch
+            // descriptor halves: everything below is 32-bit adds on the low word (units of 16 bytes)
+            const uint32_t dhi = umma_desc_hi(row_bytes);
+            const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
+            const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4, a_sub16 = p.a_sub_bytes >> 4;
+            const uint32_t a_shift16 = patch ? (p.tw * row_bytes) >> 4 : 0;  // between vertical taps inside a patch
+            const uint32_t idesc = p.idesc;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -250,28 +269,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t accum = 0;
                 for (int g = 0; g < num_groups; ++g) {
                     mbar_wait(&a_full[as], aph);
-                    const uint32_t a_addr = smem_u32(sA + as * p.a_stage_bytes);
+                    uint32_t a_lo = a_base + as * a_stage16;
                     for (int j = 0; j < grp; ++j) {
                         mbar_wait(&b_full[bs], bph);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(sB + bs * p.b_stage_bytes);
-                        for (int k = 0; k < k_steps; ++k) {
-                            const uint64_t bd = umma_smem_desc(b_addr + k * 32, row_bytes);
+                        const uint32_t b_lo = b_base + bs * b_stage16;
+                        if (elect_one()) {
 #pragma unroll
-                            for (int mi = 0; mi < MT; ++mi) {
-                                const uint64_t ad = umma_smem_desc(a_addr + mi * p.a_sub_bytes + j * a_shift + k * 32, row_bytes);
-                                umma_f16_ss(d_tmem + mi * BLOCK_N, ad, bd, p.idesc, accum);
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < k_steps) {
+#pragma unroll
+                                    for (int mi = 0; mi < MT; ++mi)
+                                        umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
+                                                         (accum | k) != 0 ? 1u : 0u);
+                                }
                             }
-                            accum = 1;
+                            if (csize == 1) umma_commit(&b_empty[bs]);
+                            else umma_commit_mcast(&b_empty[bs], cmask);
+                            if (j == grp - 1) umma_commit(&a_empty[as]);
+                            if (j == grp - 1 && g == num_groups - 1) umma_commit(&tmem_full[acc]);
                         }
-                        if (csize == 1) umma_commit(&b_empty[bs]);
-                        else umma_commit_mcast(&b_empty[bs], cmask);
+                        __syncwarp();
+                        accum = 1;
                         if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        a_lo += a_shift16;
                     }
-                    umma_commit(&a_empty[as]);
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -286,7 +310,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int slot = ew >> 2;                 // 0..3
         const int row = quarter * 32 + lane;      // accumulator row (= TMEM lane) owned by this thread
         const bool bf16 = p.is_bf16 != 0;
-        int acc = 0;
+        int acc = 0, head_set = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int ms = (tile / p.num_n_tiles) * csize + crank;
@@ -359,8 +383,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // this warp is done with the accumulator set
             } else {
-                // ---- Detect head (models/yolo.py:95-113): N tile `nt` == anchor; pass 0 raw logits, pass 1 decoded ----
-                uint16_t* stage = reinterpret_cast<uint16_t*>(smem + L.off_out);  // [128 rows][no]: the exact global layout
+                // ---- Detect head (models/yolo.py:95-113): N tile `nt` == anchor.  One TMEM pass produces the raw logits AND
+                // the decoded predictions into two smem blocks laid out exactly like their global destinations
+                // ([128 pixels][no] contiguous per anchor), one block barrier, then 16-byte vector copy-out.  Two staging
+                // sets alternate per tile, so the barrier of tile i+1 also fences the reuse of tile i-1's set.
+                const uint32_t blk = (kBlockM * p.no * 2 + 1023) & ~1023u;
+                const int set = head_set;
+                head_set ^= 1;
+                uint16_t* stage_raw = reinterpret_cast<uint16_t*>(smem + L.off_out + (2 * set) * blk);
+                uint16_t* stage_z = reinterpret_cast<uint16_t*>(smem + L.off_out + (2 * set + 1) * blk);
                 const int no = p.no;
                 const int a = nt;
                 const int m0 = ms * kBlockM;
@@ -369,47 +400,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < p.M) { const int pix = m % p.HoWo; gy = pix / p.nx; gx = pix - gy * p.nx; }
                 const int rows_here = min(kBlockM, p.M - m0);
                 const int b_lo = m0 / p.HoWo, b_hi = (m0 + rows_here - 1) / p.HoWo;
-                named_bar_sync(1, kEpiThreads);  // previous tile's copy-out finished: the staging block may be rewritten
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (slot * 32 < no) {
-                        const int c = slot;
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_row + c * 32, v);
-                        tmem_ld_wait();
+                if (slot * 32 < no) {
+                    const int c = slot;
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    const float fgx = static_cast<float>(gx) - 0.5f, fgy = static_cast<float>(gy) - 0.5f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int o = c * 32 + j;
-                            if (o < no) {
-                                float x = __uint_as_float(v[j]) + sBias[n0 + o];
-                                if (pass == 1 && o < 5 + p.nc) {
-                                    const float s = sigmoid_f(x);
-                                    if (o == 0) x = (s * 2.0f + (static_cast<float>(gx) - 0.5f)) * p.det_stride;
-                                    else if (o == 1) x = (s * 2.0f + (static_cast<float>(gy) - 0.5f)) * p.det_stride;
-                                    else if (o < 4) { const float t = s * 2.0f; x = t * t * p.anchor_wh[a * 2 + (o - 2)]; }
-                                    else x = s;
-                                }
-                                stage[row * no + o] = pack1(x, bf16);
+                    for (int j = 0; j < 32; ++j) {
+                        const int o = c * 32 + j;
+                        if (o < no) {
+                            const float x = __uint_as_float(v[j]) + sBias[n0 + o];
+                            float d = x;
+                            if (o < 5 + p.nc) {
+                                const float sg = sigmoid_f(x);
+                                if (o == 0) d = (sg * 2.0f + fgx) * p.det_stride;
+                                else if (o == 1) d = (sg * 2.0f + fgy) * p.det_stride;
+                                else if (o < 4) { const float t = sg * 2.0f; d = t * t * p.anchor_wh[a * 2 + (o - 2)]; }
+                                else d = sg;
                             }
+                            stage_raw[row * no + o] = pack1(x, bf16);
+                            stage_z[row * no + o] = pack1(d, bf16);
                         }
                     }
-                    if (pass == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                    }
-                    named_bar_sync(1, kEpiThreads);
-                    // copy out: for each image the tile touches, rows [r_lo, r_hi) are one contiguous global block
-                    for (int b = b_lo; b <= b_hi; ++b) {
-                        const int r_lo = max(b * p.HoWo - m0, 0), r_hi = min((b + 1) * p.HoWo - m0, rows_here);
-                        const int pix_lo = m0 + r_lo - b * p.HoWo;
-                        const long long dst_el = pass == 0
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                named_bar_sync(1, kEpiThreads);
+                // copy out: for each image the tile touches, rows [r_lo, r_hi) are one contiguous global block per output
+                for (int b = b_lo; b <= b_hi; ++b) {
+                    const int r_lo = max(b * p.HoWo - m0, 0), r_hi = min((b + 1) * p.HoWo - m0, rows_here);
+                    const int pix_lo = m0 + r_lo - b * p.HoWo;
+                    const int n_el = (r_hi - r_lo) * no;
+#pragma unroll
+                    for (int which = 0; which < 2; ++which) {
+                        const long long dst_el = which == 0
                             ? ((static_cast<long long>(b) * p.na + a) * p.HoWo + pix_lo) * no
                             : (static_cast<long long>(b) * p.z_rows + p.z_row0 + static_cast<long long>(a) * p.HoWo + pix_lo) * no;
-                        uint16_t* dst = reinterpret_cast<uint16_t*>(pass == 0 ? p.raw : p.z) + dst_el;
-                        const uint16_t* src = stage + r_lo * no;
-                        const int n_el = (r_hi - r_lo) * no;
+                        uint16_t* dst = reinterpret_cast<uint16_t*>(which == 0 ? p.raw : p.z) + dst_el;
+                        const uint16_t* src = (which == 0 ? stage_raw : stage_z) + r_lo * no;
                         if ((((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) && (n_el & 7) == 0) {
                             const uint4* s4 = reinterpret_cast<const uint4*>(src);
                             uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -418,7 +450,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = et; i < n_el; i += kEpiThreads) dst[i] = src[i];
                         }
                     }
-                    if (pass == 0) named_bar_sync(1, kEpiThreads);
                 }
             }
             if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
