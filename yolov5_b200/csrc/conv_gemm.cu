@@ -310,6 +310,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int slot = ew >> 2;                 // 0..3
         const int row = quarter * 32 + lane;      // accumulator row (= TMEM lane) owned by this thread
         const bool bf16 = p.is_bf16 != 0;
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int tw_shift = patch ? __ffs(p.tw) - 1 : 0;
+        const int ry = row >> tw_shift, rx = row & ((1 << tw_shift) - 1);
         int acc = 0, head_set = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -328,11 +331,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int mt = ms * MT + mi;
                     long long gpix = -1;                          // global output pixel of this thread's row
                     if (patch) {
-                        const int per_img = p.tiles_x * p.tiles_y;
+                        // warp-uniform tile decode (two divisions per chunk); the thread's offset inside the th x tw tile
+                        // (ry, rx) is loop invariant because tw is a power of two
                         const int img = mt / per_img;
                         const int rem = mt - img * per_img;
                         const int tyi = rem / p.tiles_x;
-                        const int oy = tyi * p.th + row / p.tw, ox = (rem - tyi * p.tiles_x) * p.tw + row % p.tw;
+                        const int oy = tyi * p.th + ry, ox = (rem - tyi * p.tiles_x) * p.tw + rx;
                         if (mt < p.num_m_tiles && oy < p.Ho && ox < p.Wo) gpix = static_cast<long long>(img) * p.HoWo + oy * p.Wo + ox;
                     } else {
                         const long long m = static_cast<long long>(mt) * kBlockM + row;
@@ -531,33 +535,23 @@ int pick_block_n(int out_c, int64_t m_rows) {
     return 128;
 }
 
-// Tile shape (block_n, mt) for out_c > 64 from a three-term model: operand bytes over the measured L2->SM rate,
-// tensor-pipe cycles (N/2 per M128xNxK16 instruction) with wave quantisation over the SMs, and a fixed cost per tile.
-void pick_tile(int out_c, int64_t m_rows, int num_kb, int block_k, double a_bytes_per_sub_kb, int* block_n, int* mt, int* cluster) {
+// Tile shape (block_n, sub-tiles per tile).  Rules measured on B200 (profiles/r01_tile_sweep.txt): narrow layers
+// always fill 128 TMEM columns (MT = 128 / block_n); for 128 output channels a 256x128 tile (one weight tile feeding two
+// sub-tiles) wins except for 1x1 convs; for >= 256 channels the double-buffered 128x256 tile wins for shifted-patch and
+// most 1x1 convs (its epilogue overlaps the next tile's MMAs), while TMA-im2col (stride-2) and very deep 1x1 convs are
+// faster with the single-buffered 256x256 tile (half the operand bytes per flop).
+void pick_tile(int out_c, int a_mode, int k_total, int* block_n, int* mt, int* cluster) {
     *cluster = 1;
     if (out_c <= 32) { *block_n = 32; *mt = 4; return; }
     if (out_c <= 64) { *block_n = 64; *mt = 2; return; }
-    const double l2_bytes_per_cycle = 3300.0;  // chip-wide, sustained (B200 measured ~6.3 TB/s at 1.9 GHz)
-    const int sms = 148;
-    const int64_t m_tiles = (m_rows + kBlockM - 1) / kBlockM;
-    double best = 1e30;
-    for (int bn : {128, 256}) {
-        if (bn == 256 && out_c <= 128) continue;
-        for (int m : {1, 2}) {
-            for (int cl : {1}) {  // {1, 2}: weight-tile multicast measured no faster on B200 (L2 dedups concurrent reads); kept selectable
-                const int64_t m_super = (m_tiles + m - 1) / m;
-                if (cl > 1 && m_super < 2 * cl) continue;
-                const int64_t tiles = ((m_super + cl - 1) / cl) * cl * ((out_c + bn - 1) / bn);  // CTA-tiles incl. cluster padding
-                const int64_t waves = (tiles + sms - 1) / sms;
-                const double bytes_per_kb = m * a_bytes_per_sub_kb + bn * block_k * 2.0 / cl;  // multicast: each CTA pulls 1/cl of B from L2
-                const double t_l2 = tiles * (double)num_kb * bytes_per_kb / l2_bytes_per_cycle;
-                const double t_mma = waves * (double)num_kb * (block_k / 16) * m * (bn / 2.0);
-                const double t_fix = waves * (2500.0 + (m * bn == 512 ? 3000.0 : 0.0)) + (cl > 1 ? 1500.0 : 0.0);
-                const double t = (t_l2 > t_mma ? t_l2 : t_mma) + t_fix;
-                if (t < best) { best = t; *block_n = bn; *mt = m; *cluster = cl; }
-            }
-        }
+    const int pad128 = (out_c + 127) / 128 * 128, pad256 = (out_c + 255) / 256 * 256;
+    if (out_c <= 128 || pad128 < pad256) {
+        *block_n = 128;
+        *mt = a_mode == A_LINEAR ? 1 : 2;
+        return;
     }
+    *block_n = 256;
+    *mt = (a_mode == A_IM2COL || (a_mode == A_LINEAR && k_total >= 2048)) ? 2 : 1;
 }
 
 CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
@@ -759,19 +753,49 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     const int64_t M64 = static_cast<int64_t>(d->batch) * g.Ho * g.Wo;
     if (M64 > 0x7fffffff - 256) return set_error(Y5_E_UNSUPPORTED, "conv: more than 2^31 output pixels");
     const int bk = d->block_k ? d->block_k : pick_block_k(d->in_c);
-    int bn = d->block_n, mt_sel = 0, cl_sel = 1;
     if (bk != 16 && bk != 32 && bk != 64) return set_error(Y5_E_INVALID, "conv: block_k must be 16/32/64");
+    const bool plain = g.kh == 1 && g.kw == 1 && d->stride == 1 && g.pad_h == 0 && g.pad_w == 0 && !d->in_x_stride && !d->in_y_stride &&
+                       !d->in_n_stride;
+    // spatial tile for PATCH mode: th x tw = 128 with tw in {8..128}; pick the shape wasting the fewest pixels
+    int best_tw = 0;
+    double best_eff = 0.0;
+    if (d->stride == 1 && !plain) {
+        for (int tw = 8; tw <= 128; tw <<= 1) {
+            const int th = 128 / tw;
+            const double eff = (double)g.Wo * g.Ho / ((double)((g.Wo + tw - 1) / tw * tw) * ((g.Ho + th - 1) / th * th));
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_tw = tw; }
+        }
+    }
+    int a_mode_sel;
+    if (plain) a_mode_sel = A_LINEAR;
+    else if (d->a_mode == 2 && d->stride != 1) return set_error(Y5_E_INVALID, "conv: patch mode needs stride 1");
+    else if (d->a_mode == 2 || (d->a_mode == 0 && d->stride == 1 && best_eff >= 0.75)) a_mode_sel = A_PATCH;
+    else a_mode_sel = A_IM2COL;
+
+    int bn = d->block_n, mt_sel = 0, cl_sel = 1;
     {
-        const int kw_ = d->kw ? d->kw : d->ksize;
-        const int num_kb = d->ksize * kw_ * ((d->in_c + bk - 1) / bk);
         int bn_auto = 0;
-        pick_tile(d->out_c, M64, num_kb, bk, 128.0 * bk * 2.0, &bn_auto, &mt_sel, &cl_sel);
+        pick_tile(d->out_c, a_mode_sel, g.kh * g.kw * d->in_c, &bn_auto, &mt_sel, &cl_sel);
         if (!bn) bn = bn_auto;
         else {  // forced block_n (tests / tuning): reserved bit 1 asks for MT = 2, bits 8.. give the cluster size
             mt_sel = bn < 128 ? 128 / bn : ((d->reserved & 2) ? 2 : 1);
             cl_sel = (d->reserved >> 8) > 1 ? (d->reserved >> 8) : 1;
         }
         if (const char* e = getenv("Y5_CLUSTER")) cl_sel = atoi(e) > 1 && bn >= 128 ? atoi(e) : 1;
+        if (const char* e = getenv("Y5_BIG_TILE")) {  // tuning: "<block_n>x<mt>" for layers with out_c >= 256, e.g. 256x1
+            int tb = 0, tm = 0;
+            if (!d->block_n && d->out_c >= 256 && sscanf(e, "%dx%d", &tb, &tm) == 2 && (tb == 128 || tb == 256) && (tm == 1 || tm == 2)) {
+                bn = tb;
+                mt_sel = tm;
+            }
+        }
+        if (const char* e = getenv("Y5_MID_TILE")) {  // same for 64 < out_c < 256: "128x1" | "128x2"
+            int tb = 0, tm = 0;
+            if (!d->block_n && d->out_c > 64 && d->out_c < 256 && sscanf(e, "%dx%d", &tb, &tm) == 2 && tb == 128 && (tm == 1 || tm == 2)) {
+                bn = tb;
+                mt_sel = tm;
+            }
+        }
         if (cl_sel != 1 && cl_sel != 2 && cl_sel != 4) cl_sel = 1;
     }
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
@@ -796,22 +820,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     p.c_chunks = (d->in_c + bk - 1) / bk;
     const int row_bytes = bk * 2;
     p.b_stage_bytes = bn * row_bytes;
-    const bool plain = g.kh == 1 && g.kw == 1 && d->stride == 1 && g.pad_h == 0 && g.pad_w == 0 && !d->in_x_stride && !d->in_y_stride &&
-                       !d->in_n_stride;
-    // spatial tile for PATCH mode: th x tw = 128 with tw in {8..128}; pick the shape wasting the fewest pixels
-    int best_tw = 0;
-    double best_eff = 0.0;
-    if (d->stride == 1 && !plain) {
-        for (int tw = 8; tw <= 128; tw <<= 1) {
-            const int th = 128 / tw;
-            const double eff = (double)g.Wo * g.Ho / ((double)((g.Wo + tw - 1) / tw * tw) * ((g.Ho + th - 1) / th * th));
-            if (eff > best_eff + 1e-9) { best_eff = eff; best_tw = tw; }
-        }
-    }
-    if (plain) p.a_mode = A_LINEAR;
-    else if (d->a_mode == 2 && d->stride != 1) { delete plan; return set_error(Y5_E_INVALID, "conv: patch mode needs stride 1"); }
-    else if (d->a_mode == 2 || (d->a_mode == 0 && d->stride == 1 && best_eff >= 0.75)) p.a_mode = A_PATCH;
-    else p.a_mode = A_IM2COL;
+    p.a_mode = a_mode_sel;
 
     const CUtensorMapSwizzle sw = swizzle_for_row_bytes(row_bytes);
     int e = 0;
