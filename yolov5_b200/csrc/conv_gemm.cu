@@ -540,7 +540,7 @@ int pick_block_n(int out_c, int64_t m_rows) {
 // sub-tiles) wins except for 1x1 convs; for >= 256 channels the double-buffered 128x256 tile wins for shifted-patch and
 // most 1x1 convs (its epilogue overlaps the next tile's MMAs), while TMA-im2col (stride-2) and very deep 1x1 convs are
 // faster with the single-buffered 256x256 tile (half the operand bytes per flop).
-void pick_tile(int out_c, int a_mode, int k_total, int* block_n, int* mt, int* cluster) {
+void pick_tile(int out_c, int a_mode, int k_total, int64_t m_tiles, int* block_n, int* mt, int* cluster) {
     *cluster = 1;
     if (out_c <= 32) { *block_n = 32; *mt = 4; return; }
     if (out_c <= 64) { *block_n = 64; *mt = 2; return; }
@@ -548,10 +548,15 @@ void pick_tile(int out_c, int a_mode, int k_total, int* block_n, int* mt, int* c
     if (out_c <= 128 || pad128 < pad256) {
         *block_n = 128;
         *mt = a_mode == A_LINEAR ? 1 : 2;
+        if (*mt == 2 && ((m_tiles + 1) / 2) * (pad128 / 128) < 120) *mt = 1;  // keep ~a wave of tiles on small maps
         return;
     }
     *block_n = 256;
     *mt = (a_mode == A_IM2COL || (a_mode == A_LINEAR && k_total >= 2048)) ? 2 : 1;
+    // small feature maps: big tiles would leave most of the 148 SMs without a tile -- shrink until ~one wave exists
+    auto tiles = [&](int bn, int m) { return ((m_tiles + m - 1) / m) * ((out_c + bn - 1) / bn); };
+    if (tiles(*block_n, *mt) < 120 && *mt == 2) *mt = 1;
+    if (tiles(*block_n, *mt) < 120) *block_n = 128;
 }
 
 CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
@@ -775,7 +780,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     int bn = d->block_n, mt_sel = 0, cl_sel = 1;
     {
         int bn_auto = 0;
-        pick_tile(d->out_c, a_mode_sel, g.kh * g.kw * d->in_c, &bn_auto, &mt_sel, &cl_sel);
+        pick_tile(d->out_c, a_mode_sel, g.kh * g.kw * d->in_c, (M64 + kBlockM - 1) / kBlockM, &bn_auto, &mt_sel, &cl_sel);
         if (!bn) bn = bn_auto;
         else {  // forced block_n (tests / tuning): reserved bit 1 asks for MT = 2, bits 8.. give the cluster size
             mt_sel = bn < 128 ? 128 / bn : ((d->reserved & 2) ? 2 : 1);

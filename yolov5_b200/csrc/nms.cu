@@ -79,13 +79,13 @@ __device__ __forceinline__ int for_each_candidate(const NmsArgs& a, int b, int s
     if (my_row < a.N) pass = ld_elem(a.pred, img_base + static_cast<long long>(my_row) * a.no + 4, a.dtype) > a.thr;
     unsigned rows = __ballot_sync(0xffffffffu, pass);
     int count = 0;
-    while (rows) {  // warp-uniform loop
-        const int rl = __ffs(rows) - 1;
-        rows &= rows - 1;
-        const int r = row0 + rl;
-        const long long rb = img_base + static_cast<long long>(r) * a.no;
-        const float obj = ld_elem(a.pred, rb + 4, a.dtype);
-        if (a.multi_label) {
+    if (a.multi_label) {
+        while (rows) {  // warp-uniform loop: one passing row at a time, lanes stride over the classes
+            const int rl = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int r = row0 + rl;
+            const long long rb = img_base + static_cast<long long>(r) * a.no;
+            const float obj = ld_elem(a.pred, rb + 4, a.dtype);
             for (int j0 = 0; j0 < a.nc; j0 += 32) {
                 const int j = j0 + lane;
                 float conf = 0.0f;
@@ -98,25 +98,40 @@ __device__ __forceinline__ int for_each_candidate(const NmsArgs& a, int b, int s
                 f(ok, conf, static_cast<unsigned>(r) * a.nc + (ok ? j : 0), count, m);
                 count += __popc(m);
             }
-        } else {
-            // best class: maximum of the rounded products, first index on ties (torch.max)
+        }
+    } else {
+        // best class per row: maximum of the rounded products, first index on ties (torch.max).  Four passing rows are
+        // handled per iteration, eight lanes each (ascending row order == ascending lane-group order, so ballot ranks stay
+        // in candidate order); this cuts the dependent load rounds per segment by 4.
+        const int sub = lane >> 3, sl = lane & 7;
+        while (rows) {
+            const unsigned rl = __fns(rows, 0, sub + 1);  // position of this group's row among the set bits (0xffffffff: none)
+            const bool has = rl < 32u;
             float best = -INFINITY;
             int bj = 0x7fffffff;
-            for (int j = lane; j < a.nc; j += 32) {
-                const float conf = rnd(__fmul_rn(ld_elem(a.pred, rb + 5 + j, a.dtype), obj), a.dtype);
-                if (bj == 0x7fffffff || conf > best) { best = conf; bj = j; }
+            int r = 0;
+            if (has) {
+                r = row0 + static_cast<int>(rl);
+                const long long rb = img_base + static_cast<long long>(r) * a.no;
+                const float obj = ld_elem(a.pred, rb + 4, a.dtype);
+                for (int j = sl; j < a.nc; j += 8) {
+                    const float conf = rnd(__fmul_rn(ld_elem(a.pred, rb + 5 + j, a.dtype), obj), a.dtype);
+                    if (bj == 0x7fffffff || conf > best) { best = conf; bj = j; }
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = 4; o > 0; o >>= 1) {  // reduce inside the 8-lane group
                 const float ob = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
                 if (oj != 0x7fffffff && (bj == 0x7fffffff || ob > best || (ob == best && oj < bj))) { best = ob; bj = oj; }
             }
-            const bool okrow = bj != 0x7fffffff && best > a.thr && class_allowed(cls_mask, bj);
-            const bool ok = okrow && lane == 0;
-            const unsigned m = okrow ? 1u : 0u;
+            const bool okrow = has && bj != 0x7fffffff && best > a.thr && class_allowed(cls_mask, bj);
+            const bool ok = okrow && sl == 0;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
             f(ok, best, static_cast<unsigned>(r) * a.nc + (okrow ? bj : 0), count, m);
-            count += okrow ? 1 : 0;
+            count += __popc(m);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rows &= rows - 1;  // drop the (up to) four rows just handled
         }
     }
     return count;
@@ -387,7 +402,8 @@ __device__ __forceinline__ bool iou_gt(const float4& p, float parea, const float
 }
 
 constexpr int kChunk = 64;
-constexpr int kGreedyThreads = 256;
+constexpr int kGreedyThreads = 1024;               // 16 threads per candidate of a chunk
+constexpr int kParts = kGreedyThreads / kChunk;    // 16
 
 // per image greedy suppression over the sorted candidates + output
 __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsArgs a) {
@@ -404,7 +420,7 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsArg
     if (t == 0) n_kept_s = 0;
     __syncthreads();
     const int ci = t & (kChunk - 1);   // candidate within chunk
-    const int part = t >> 6;           // 0..3
+    const int part = t >> 6;           // 0..15
     for (int c0 = 0; c0 < n; c0 += kChunk) {
         const int n_kept = n_kept_s;
         if (n_kept >= a.max_det) break;
@@ -418,18 +434,18 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsArg
         // (1) against the kept list: kept box i suppresses me when IoU(kept_i, me) > thr
         bool dead = false;
         if (in_range) {
-            for (int k = part; k < n_kept && !dead; k += 4) {
+            for (int k = part; k < n_kept && !dead; k += kParts) {
                 const float4 kb = kept_box[k];
                 const float karea = __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y));
                 dead = iou_gt(kb, karea, me, a.iou_thr);
             }
         }
-        if (dead || !in_range) atomicAnd(&alive_w[ci >> 5], ~(1u << (ci & 31)));
+        if (dead || (!in_range && part == 0)) atomicAnd(&alive_w[ci >> 5], ~(1u << (ci & 31)));
         // (2) pairwise inside the chunk: bit j of mask[i] set when earlier candidate j (j < i) would suppress i
         if (in_range) {
             unsigned long long m = 0ull;
-            const int j0 = part * 16;
-            for (int j = j0; j < j0 + 16 && j < ci; ++j) {
+            const int j0 = part * (kChunk / kParts);
+            for (int j = j0; j < j0 + kChunk / kParts && j < ci; ++j) {
                 const float4 ob = sb[c0 + j];
                 const float oarea = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
                 if (iou_gt(ob, oarea, me, a.iou_thr)) m |= 1ull << j;
@@ -437,19 +453,27 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const NmsArg
             if (m) atomicOr(&mask[ci], m);
         }
         __syncthreads();
-        // (3) serial resolve by one thread: registers only
-        if (t == 0) {
+        // (3) serial resolve inside warp 0: lane l holds the masks of candidates l and l+32; every lane runs the same
+        // 64-step recurrence on broadcast values (registers + shuffles only)
+        if (t < 32) {
+            const unsigned long long m_lo = mask[t], m_hi = mask[t + 32];
             const unsigned long long alive = static_cast<unsigned long long>(alive_w[0]) | (static_cast<unsigned long long>(alive_w[1]) << 32);
             unsigned long long keptbits = 0ull;
             int nk = n_kept;
-            for (int i = 0; i < kChunk && nk < a.max_det; ++i) {
-                if (((alive >> i) & 1ull) && (mask[i] & keptbits) == 0ull) {
+#pragma unroll 8
+            for (int i = 0; i < kChunk; ++i) {
+                const unsigned long long mi = __shfl_sync(0xffffffffu, i < 32 ? m_lo : m_hi, i & 31);
+                if (((alive >> i) & 1ull) && (mi & keptbits) == 0ull && nk < a.max_det) {
                     keptbits |= 1ull << i;
-                    kept_pos[nk] = c0 + i;
                     ++nk;
                 }
             }
-            n_kept_s = nk;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = t + 32 * h;
+                if ((keptbits >> i) & 1ull) kept_pos[n_kept + __popcll(keptbits & ((1ull << i) - 1ull))] = c0 + i;
+            }
+            if (t == 0) n_kept_s = nk;
         }
         __syncthreads();
         const int nk2 = n_kept_s;
