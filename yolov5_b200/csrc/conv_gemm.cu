@@ -163,6 +163,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias preload of constant weights) may
+    // overlap the tail of the previous kernel in the stream; activations are only touched after this point.
+    griddep_wait();
+    griddep_launch_dependents();
 
     // tiles are (group of csize M super-tiles, N tile); this CTA takes super-tile group*csize + crank
     const int num_tiles = ((p.num_m_super + static_cast<int>(csize) - 1) / static_cast<int>(csize)) * p.num_n_tiles;
@@ -614,22 +618,28 @@ cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvPa
     });
     if (attr_err != cudaSuccess) return attr_err;
     count_launch();
-    if (cluster <= 1) {
-        conv_gemm_kernel<BN, EPI, MT><<<grid, kThreads, smem, st>>>(a, b, p);
-        return cudaGetLastError();
-    }
+    static const bool pdl = [] { const char* e = getenv("Y5_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, MT>, a, b, p);
 }
 
