@@ -203,6 +203,54 @@ int y5_loss_fwd_bwd(const y5_loss_params* p, const void* const* pl, const float*
 int y5_loss_read_targets(const y5_loss_params* p, const void* workspace, int32_t level, int64_t* idx5_host,
                          float* tbox_host, int32_t* count_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-mode Conv = SiLU(BN(conv(x)))  (reference models/common.py:86-88; gradients of the same).
+ * Forward:   y = conv(x, W)            -> y5_conv_bn_silu_fwd with act = Y5_ACT_NONE and a zero bias (same kernel)
+ *            mean/invstd = stats(y)    -> y5_bn_stats      (also updates running_mean / running_var, momentum 0.03)
+ *            z = act(bn(y))            -> y5_bn_act_fwd
+ * Backward:  dy, dgamma, dbeta         -> y5_bn_act_bwd
+ *            dW                        -> y5_conv_wgrad    (tcgen05, MN-major operands straight from NHWC)
+ *            dx = conv(dy, W^T flipped)-> y5_conv_bn_silu_fwd again on transposed/flipped packed weights (stride-2
+ *                                         layers first expand dy with y5_zero_stuff2x); `residual` = dx accumulates.
+ * Detect.m[i] (models/yolo.py:97) has a bias and no BN: its bias gradient is y5_col_sum(dy).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct y5_wgrad_desc {
+    const void* in;       /* x view, NHWC: element (n,y,x,c) at ((n*in_h + y)*in_w + x)*in_pitch + c */
+    int32_t in_pitch;
+    int32_t batch, in_h, in_w, in_c;
+    const void* dout;     /* dy view [batch*Ho*Wo][out_c], row pitch dout_pitch elements */
+    int32_t dout_pitch;
+    int32_t out_c;
+    float* dweight;       /* fp32 [out_c][ksize][ksize][in_c] (KRSC); zeroed by the call unless accumulate != 0 */
+    int32_t ksize, stride, pad;
+    int32_t dtype;        /* Y5_F16 | Y5_BF16 (x and dy) */
+    int32_t accumulate;
+    int32_t reserved;
+} y5_wgrad_desc;
+int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream);
+
+/* workspace for y5_bn_stats / y5_bn_act_bwd / y5_col_sum: 2 * channels doubles */
+int64_t y5_bn_workspace_bytes(int32_t channels);
+/* per-channel batch mean and 1/sqrt(biased var + eps) of a [rows][channels] view; running stats (nullable) updated as
+ * nn.BatchNorm2d does (unbiased variance). */
+int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, float eps, float momentum,
+                float* mean, float* invstd, float* running_mean, float* running_var, void* workspace, void* stream);
+/* z = act(gamma * (y - mean) * invstd + beta), act: Y5_ACT_NONE | Y5_ACT_SILU; z may be a channel-slice view */
+int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int64_t rows, int32_t channels,
+                  int32_t dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                  int32_t act, void* stream);
+/* given dz: dy (gradient w.r.t. the conv output), dgamma, dbeta (fp32, overwritten) */
+int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* dz, int32_t dz_pitch, void* dy, int32_t dy_pitch,
+                  int64_t rows, int32_t channels, int32_t dtype, const float* mean, const float* invstd,
+                  const float* gamma, const float* beta, int32_t act, float* dgamma, float* dbeta, void* workspace,
+                  void* stream);
+/* out[c] = sum over rows of y[row][c] (fp32) */
+int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, float* out, void* workspace,
+               void* stream);
+/* y[n, 2i, 2j, :] = x[n, i, j, :], other pixels of the (2h, 2w) output zero */
+int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int32_t batch, int32_t h, int32_t w,
+                    int32_t c, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

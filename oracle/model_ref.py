@@ -29,6 +29,7 @@ import torch
 import torch.nn.functional as F
 
 BN_EPS = 1e-3  # set by ultralytics initialize_weights (reference models/yolo.py:259)
+_BN_BATCH_STATS = False  # forward(..., bn_batch_stats=True): BatchNorm normalises with batch statistics (module.train())
 
 
 def make_divisible(x: float, d: int) -> int:
@@ -92,7 +93,10 @@ def conv_block(sd, p, x, k=1, s=1, pad=None, fused=False, act=True):
             y = F.conv2d(x, w2, b2, stride=s, padding=pad)
         else:
             y = F.conv2d(x, w, None, stride=s, padding=pad)
-            y = F.batch_norm(y, m, v, g, b, training=False, eps=BN_EPS)
+            if _BN_BATCH_STATS:  # nn.BatchNorm2d in training mode (models/common.py:86-88 under model.train())
+                y = F.batch_norm(y, None, None, g, b, training=True, eps=BN_EPS)
+            else:
+                y = F.batch_norm(y, m, v, g, b, training=False, eps=BN_EPS)
     else:  # a state_dict taken from an already fused reference model: conv has a bias, no bn keys
         y = F.conv2d(x, w, sd[f"{p}.conv.bias"], stride=s, padding=pad)
     return F.silu(y) if act else y
@@ -173,7 +177,17 @@ def model_strides(cfg: dict) -> list[float]:
     raise ValueError("model has no Detect/Segment layer")
 
 
-def forward(cfg: dict, sd: dict, x: torch.Tensor, training: bool = False, fused: bool = False, ch: int = 3):
+def forward(cfg: dict, sd: dict, x: torch.Tensor, training: bool = False, fused: bool = False, ch: int = 3, bn_batch_stats: bool = False):
+    """See _forward; ``bn_batch_stats`` evaluates every BatchNorm with batch statistics (the training-mode forward)."""
+    global _BN_BATCH_STATS
+    prev, _BN_BATCH_STATS = _BN_BATCH_STATS, bool(bn_batch_stats)
+    try:
+        return _forward(cfg, sd, x, training, fused, ch)
+    finally:
+        _BN_BATCH_STATS = prev
+
+
+def _forward(cfg: dict, sd: dict, x: torch.Tensor, training: bool = False, fused: bool = False, ch: int = 3):
     """Whole-model forward on CPU fp32 tensors.
 
     eval Detect : (z (B,N,no), [raw_i (B,na,ny,nx,no)])          models/yolo.py:115

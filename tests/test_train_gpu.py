@@ -1,0 +1,232 @@
+"""-m gpu parity tests of the training path: weight-gradient GEMM (MN-major tcgen05), BatchNorm/SiLU training kernels, the
+Conv layer's forward/backward and a whole-model training step, against torch autograd on the same seeded data.
+
+Tolerances: activations and activation gradients are fp16/bf16 (rounding 2^-11 / 2^-8 relative per op); statistics and
+weight gradients accumulate in fp32.  Kernel-level checks are against float64 math on the same rounded inputs;
+model-level checks use the criterion of test_model_gpu.py: err(engine vs fp32 oracle) <= 1e-3*scale + 1.5*err(torch AMP
+vs fp32 oracle)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import loss_ref, model_ref
+from yolov5_b200 import _lib, train_ops
+from yolov5_b200.cfg import HYP_SCRATCH_LOW, model_cfg
+from yolov5_b200.models.common import Conv
+from yolov5_b200.models.yolo import DetectionModel
+from yolov5_b200.utils.loss import ComputeLoss
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl_rand(shape, dtype, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = ((torch.rand(*shape, generator=g) * 2 - 1) * scale).to(dtype)
+    return x.to(dev).contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,k,s,p", [
+    (2, 16, 16, 64, 128, 1, 1, 0),    # plain 2-D tiles, one co tile
+    (1, 20, 20, 32, 32, 1, 1, 0),     # channel counts below one 64-block (TMA zero fill)
+    (2, 8, 8, 256, 512, 1, 1, 0),     # four 64-channel blocks per tile, four co tiles
+    (1, 12, 12, 320, 80, 1, 1, 0),    # 5 blocks -> two ci tiles (3 + 2), co tail
+    (2, 16, 16, 64, 64, 3, 1, 1),     # hardware im2col, 9 taps
+    (1, 10, 14, 48, 96, 3, 1, 1),     # pixel count not a multiple of 64, odd widths
+    (2, 16, 16, 32, 64, 3, 2, 1),     # stride 2
+    (3, 40, 40, 128, 128, 3, 1, 1),   # several pixel ranges per tile
+])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv_wgrad_matches_float64(cuda, B, H, W, cin, cout, k, s, p, dtype):
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    x = _cl_rand((B, cin, H, W), dtype, cuda, 1)
+    dy = _cl_rand((B, cout, Ho, Wo), dtype, cuda, 2)
+    got = train_ops.conv_wgrad(x, dy, k, s, p)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, k, k), dy.double(), stride=s, padding=p)
+    err = float((got.double() - ref).abs().max() / ref.abs().max())
+    assert got.shape == ref.shape and err < 2e-5, err  # exact products, fp32 accumulation
+
+
+@pytest.mark.parametrize("k,s,p,H", [(1, 1, 0, 12), (3, 1, 1, 12), (3, 2, 1, 16)])
+def test_conv_dgrad_matches_float64(cuda, k, s, p, H):
+    dtype = torch.float16
+    cin, cout, B = 64, 96, 2
+    Ho = (H + 2 * p - k) // s + 1
+    g = torch.Generator().manual_seed(3)
+    w = (torch.rand(cout, cin, k, k, generator=g) - 0.5).to(cuda)
+    dy = _cl_rand((B, cout, Ho, Ho), dtype, cuda, 4)
+    got = train_ops.conv_dgrad(dy, w, k, s, p, (H, H))
+    ref = torch.nn.grad.conv2d_input((B, cin, H, H), w.to(dtype).double(), dy.double(), stride=s, padding=p)
+    err = float((got.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-3, err  # one fp16 rounding of the result
+
+
+@pytest.mark.parametrize("C_,rows_hw", [(32, (2, 40, 40)), (48, (1, 7, 9)), (256, (3, 20, 20)), (320, (2, 10, 10))])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
+    lib = _lib.lib()
+    B, H, W = rows_hw
+    rows = B * H * W
+    code = _lib.dtype_code(dtype)
+    st = C.c_void_p(_lib.stream_ptr(cuda))
+    y = _cl_rand((B, C_, H, W), dtype, cuda, 5, scale=2.0) + 0.25
+    y = y.contiguous(memory_format=torch.channels_last)
+    g = torch.Generator().manual_seed(6)
+    gamma = (torch.rand(C_, generator=g) + 0.5).to(cuda)
+    beta = (torch.rand(C_, generator=g) - 0.5).to(cuda)
+    rm, rv = torch.zeros(C_, device=cuda), torch.ones(C_, device=cuda)
+    mean, invstd = torch.empty(C_, device=cuda), torch.empty(C_, device=cuda)
+    ws = torch.empty(2 * C_, dtype=torch.float64, device=cuda)
+    _lib.check(lib.y5_bn_stats(y.data_ptr(), C_, rows, C_, code, 1e-3, 0.03, mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                               ws.data_ptr(), st))
+    yd = y.double().permute(0, 2, 3, 1).reshape(rows, C_)
+    m_ref, v_ref = yd.mean(0), yd.var(0, unbiased=False)
+    assert torch.allclose(mean.double(), m_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(invstd.double(), 1 / torch.sqrt(v_ref + 1e-3), rtol=1e-5)
+    assert torch.allclose(rm.double(), 0.03 * m_ref, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(rv.double(), 0.97 + 0.03 * yd.var(0, unbiased=True), rtol=1e-5)
+    # forward: same rounding points as torch autocast (BN result rounded, SiLU of the rounded value)
+    z = torch.empty_like(y)
+    _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                 beta.data_ptr(), 1, st))
+    u = ((y.float() - mean.view(1, -1, 1, 1)) * (invstd * gamma).view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)).to(dtype)
+    z_ref = F.silu(u.float()).to(dtype)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert float((z.float() - z_ref.float()).abs().max()) <= 2 * ulp * float(z_ref.float().abs().max())
+    # backward against fp32 autograd of the unrounded composite
+    dz = _cl_rand((B, C_, H, W), dtype, cuda, 7)
+    dy = torch.empty_like(y)
+    dg, db = torch.empty(C_, device=cuda), torch.empty(C_, device=cuda)
+    _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), C_, dz.data_ptr(), C_, dy.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(),
+                                 gamma.data_ptr(), beta.data_ptr(), 1, dg.data_ptr(), db.data_ptr(), ws.data_ptr(), st))
+    yf = y.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = F.silu(F.batch_norm(yf, None, None, gf, bf, training=True, eps=1e-3))
+    out.backward(dz.float())
+    tol = 6e-3 if dtype == torch.float16 else 4e-2
+    for a, b in ((dy.float(), yf.grad), (dg, gf.grad), (db, bf.grad)):
+        assert float((a - b).abs().max()) <= tol * float(b.abs().max()), (float((a - b).abs().max()), float(b.abs().max()))
+
+
+def test_col_sum_and_zero_stuff(cuda):
+    lib = _lib.lib()
+    st = C.c_void_p(_lib.stream_ptr(cuda))
+    x = _cl_rand((2, 40, 6, 10), torch.float16, cuda, 8)
+    out = torch.empty(40, device=cuda)
+    ws = torch.empty(80, dtype=torch.float64, device=cuda)
+    _lib.check(lib.y5_col_sum(x.data_ptr(), 40, 120, 40, _lib.Y5_F16, out.data_ptr(), ws.data_ptr(), st))
+    assert torch.allclose(out.double(), x.double().sum((0, 2, 3)), rtol=1e-6, atol=1e-6)
+    z = torch.empty(2, 40, 12, 20, dtype=torch.float16, device=cuda).contiguous(memory_format=torch.channels_last)
+    _lib.check(lib.y5_zero_stuff2x(x.data_ptr(), 40, z.data_ptr(), 40, 2, 6, 10, 40, _lib.Y5_F16, st))
+    ref = torch.zeros_like(z)
+    ref[:, :, ::2, ::2] = x
+    assert torch.equal(z, ref)
+
+
+@pytest.mark.parametrize("k,s", [(1, 1), (3, 1), (3, 2)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_conv_layer_train_forward_backward(cuda, k, s, dtype):
+    """Conv(c1,c2,k,s).train() under autocast: output, running stats and all four gradients vs torch fp32 autograd."""
+    torch.manual_seed(0)
+    c1, c2, B, H = 32, 64, 4, 16
+    m = Conv(c1, c2, k, s).to(cuda)
+    m.bn.eps, m.bn.momentum = 1e-3, 0.03
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5)
+        m.bn.bias.uniform_(-0.5, 0.5)
+    m.train()
+    x = _cl_rand((B, c1, H, H), dtype, cuda, 9).requires_grad_(True)
+    with torch.autocast("cuda", dtype=dtype):
+        z = m(x)
+    dz = _cl_rand(tuple(z.shape), dtype, cuda, 10)
+    z.backward(dz)
+    # reference: plain torch, fp32 math on the same (rounded) input and weights rounded like autocast does
+    w = m.conv.weight.detach().to(dtype).float().requires_grad_(True)
+    g, b_ = m.bn.weight.detach().clone().requires_grad_(True), m.bn.bias.detach().clone().requires_grad_(True)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, w, None, stride=s, padding=k // 2)
+    zr = F.silu(F.batch_norm(yr, None, None, g, b_, training=True, eps=1e-3))
+    zr.backward(dz.float())
+    tol = 8e-3 if dtype == torch.float16 else 6e-2
+
+    def close(a, b, name):
+        e, sc = float((a.detach().float() - b).abs().max()), float(b.abs().max())
+        assert e <= tol * sc, (name, e, sc)
+
+    close(z, zr.detach(), "z")
+    close(x.grad, xr.grad, "dx")
+    close(m.conv.weight.grad, w.grad, "dw")
+    close(m.bn.weight.grad, g.grad, "dgamma")
+    close(m.bn.bias.grad, b_.grad, "dbeta")
+    yd = yr.detach().permute(1, 0, 2, 3).reshape(c2, -1)
+    assert torch.allclose(m.bn.running_mean, 0.03 * yd.mean(1), atol=2e-3)
+    assert int(m.bn.num_batches_tracked) == 1
+
+
+def _ref_train_step(cfg, sd, img, targets, dev, autocast_dtype):
+    """torch reference of one training forward/backward (oracle model with batch-stat BN + oracle loss)."""
+    params = {k: v.to(dev).clone().requires_grad_(v.is_floating_point() and "running" not in k and "anchors" not in k) for k, v in sd.items()}
+    x = img.to(dev).float() / 255 if img.dtype == torch.uint8 else img.to(dev).float()
+    ctx = torch.autocast("cuda", dtype=autocast_dtype) if autocast_dtype is not None else torch.autocast("cuda", enabled=False)
+    with ctx:
+        p = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+    loss, items = loss_ref.compute_loss([q.float().cpu() for q in p], targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)  # CPU oracle
+    loss.backward()
+    grads = {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
+    return [q.detach() for q in p], loss.detach(), grads
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_model_training_step_yolov5n(cuda, dtype):
+    """DetectionModel('yolov5n').train(): raw head maps, loss and parameter gradients of one step vs the fp32 oracle,
+    judged against torch's own autocast execution of the reference expressions."""
+    name, shape = "yolov5n", (4, 3, 128, 128)
+    cfg = model_cfg(name)
+    sd = model_ref.synth_state_dict(cfg, seed=21)
+    g = torch.Generator().manual_seed(22)
+    img = (torch.rand(*shape, generator=g) * 255).to(torch.uint8)
+    targets = torch.from_numpy(loss_ref.synth_targets(shape[0], seed=23)).float()
+    p32, loss32, g32 = _ref_train_step(cfg, sd, img, targets, cuda, None)
+    pamp, lossamp, gamp = _ref_train_step(cfg, sd, img, targets, cuda, dtype)
+
+    m = DetectionModel(name)
+    m.load_state_dict(sd)
+    m = m.to(cuda).train()
+    m.hyp = dict(HYP_SCRATCH_LOW)
+    compute_loss = ComputeLoss(m)
+    with torch.autocast("cuda", dtype=dtype):
+        p = m(img.to(cuda))
+    assert [tuple(q.shape) for q in p] == [tuple(q.shape) for q in p32]
+    for l, (a, r, lo) in enumerate(zip(p, p32, pamp)):
+        sc = float(r.abs().max())
+        e, el = float((a.detach().float() - r).abs().max()), float((lo.float() - r).abs().max())
+        assert e <= 1e-3 * sc + 1.5 * el, ("raw", l, e / sc, el / sc)
+    loss, items = compute_loss(p, targets.to(cuda))  # the product loss kernel (parity-tested in test_loss_gpu.py)
+    loss.backward()
+    assert abs(float(loss) - float(loss32)) <= 1e-3 * abs(float(loss32)) + 1.5 * abs(float(lossamp) - float(loss32))
+    named = dict(m.named_parameters())
+    # per parameter tensor: relative L2 error of the gradient vs the fp32 oracle, mine and torch-AMP's.  Both are noisy
+    # low-precision evaluations of the same expressions, so the engine is judged against AMP's own error: never more
+    # than 2.5x on any tensor (single-sample noise), not worse on the whole (median ratio), and close in aggregate.
+    ratios, mine_sq, amp_sq, ref_sq = [], 0.0, 0.0, 0.0
+    worst = (0.0, None)
+    for k, gr in g32.items():
+        got = named[k].grad
+        assert got is not None, k
+        n = float(gr.norm())
+        if n == 0:
+            continue
+        e, el = float((got.float() - gr).norm()) / n, float((gamp[k].float() - gr).norm()) / n
+        mine_sq, amp_sq, ref_sq = mine_sq + (e * n) ** 2, amp_sq + (el * n) ** 2, ref_sq + n * n
+        r = e / (1e-3 + el)
+        ratios.append(r)
+        if r > worst[0]:
+            worst = (r, k, e, el)
+    ratios.sort()
+    summary = dict(n=len(ratios), median=ratios[len(ratios) // 2], worst=worst, total_mine=(mine_sq / ref_sq) ** 0.5,
+                   total_amp=(amp_sq / ref_sq) ** 0.5)
+    print("train-step gradient report", dtype, summary)
+    assert len(ratios) > 150, summary
+    assert worst[0] <= 2.5 and summary["median"] <= 1.25, summary
+    assert summary["total_mine"] <= 1e-3 + 1.5 * summary["total_amp"], summary

@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liby5b200.so")
+LIB_PATH = os.environ.get("Y5B200_LIB") or os.path.join(_HERE, "liby5b200.so")  # env override: A/B experiments only
 
 Y5_F16, Y5_BF16, Y5_F32, Y5_U8 = 0, 1, 2, 3
 ACT_NONE, ACT_SILU = 0, 1
@@ -74,6 +74,17 @@ class LossParams(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p), ("in_pitch", C.c_int32),
+        ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("in_c", C.c_int32),
+        ("dout", C.c_void_p), ("dout_pitch", C.c_int32), ("out_c", C.c_int32),
+        ("dweight", C.c_void_p),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("dtype", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 # name -> (restype, argtypes); mirrors include/y5b200.h one to one (tests/test_abi.py checks the header against this)
@@ -102,6 +113,13 @@ SIGNATURES = {
     "y5_loss_workspace_bytes": (_I64, [C.POINTER(LossParams)]),
     "y5_loss_fwd_bwd": (_I32, [C.POINTER(LossParams), C.POINTER(_P), _P, _P, _P, C.POINTER(_P), _P, _I64, _P]),
     "y5_loss_read_targets": (_I32, [C.POINTER(LossParams), _P, _I32, _P, _P, _P, _P]),
+    "y5_conv_wgrad": (_I32, [C.POINTER(WgradDesc), _P]),
+    "y5_bn_workspace_bytes": (_I64, [_I32]),
+    "y5_bn_stats": (_I32, [_P, _I32, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "y5_bn_act_fwd": (_I32, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P]),
+    "y5_bn_act_bwd": (_I32, [_P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "y5_col_sum": (_I32, [_P, _I32, _I64, _I32, _I32, _P, _P, _P]),
+    "y5_zero_stuff2x": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
 }
 
 _lib = None

@@ -24,7 +24,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = {
     "host_util.cu": [],
     "conv_gemm.cu": [],
+    "conv_wgrad.cu": [],
     "aux_kernels.cu": [],
+    "train_kernels.cu": [],
     "nms.cu": ["-fmad=false"],
     "loss.cu": ["-fmad=false"],
 }

@@ -232,7 +232,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 // ---------------------------------------------------------------------------------------------------------------------
 // numeric helpers
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef Y5_SILU_EXACT
+// x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op per element (tanh.approx, rel. error 2^-11) instead of two
+// (ex2 + rcp).  Measured on B200: model outputs' error against the fp32 oracle is unchanged to 3 digits in fp16 and
+// bf16 (tools/accuracy_report.py) -- the result is rounded to 11 / 8 significant bits right after -- and the forward
+// is 2-3 % faster.  -DY5_SILU_EXACT restores the ex2 + rcp form.
+__device__ __forceinline__ float silu_f(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+#else
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+#endif
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, bool bf16) {

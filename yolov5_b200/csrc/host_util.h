@@ -21,4 +21,15 @@ using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 EncodeTiledFn driver_fn_encode_tiled();
 EncodeIm2colFn driver_fn_encode_im2col();
 
+
+CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes);
+CUtensorMapDataType tm_dtype(int dtype);
+// tiled tensor map of `rank` dims (innermost first); on failure records a message and returns Y5_E_DRIVER
+int encode_tiled(CUtensorMap* map, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                 const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what);
+// im2col tensor map over an NHWC view (element strides xs/ys/ns), filter kh x kw, conv stride / padding
+int encode_im2col(CUtensorMap* map, int dtype, const void* base, int C, int W, int H, int N, long long xs, long long ys, long long ns,
+                  int kh, int kw, int stride, int pad_h, int pad_w, uint32_t channels_per_pixel, uint32_t pixels_per_column,
+                  CUtensorMapSwizzle sw);
+
 }  // namespace y5

@@ -1,8 +1,8 @@
 """Layer zoo of the hot path with the reference's class names, constructor signatures, attribute names and
 state_dict keys (reference models/common.py:62-92,164-181,230-246,318-340,443-453,1104-1117), so checkpoints and
 state_dicts move between the two unchanged.  The modules only *hold* parameters: executing one (``forward``) lowers it
-to liby5b200 kernels through yolov5_b200.engine.Program -- there is no torch.nn arithmetic behind them and CPU
-tensors are rejected.
+to liby5b200 kernels through yolov5_b200.engine.Program (eval) or yolov5_b200.train_ops (training: batch-statistics
+BatchNorm, autograd) -- there is no torch.nn convolution behind them and CPU tensors are rejected.
 """
 from __future__ import annotations
 
@@ -29,8 +29,12 @@ class _EngineLayer(nn.Module):
             raise RuntimeError(
                 f"y5b200: {type(self).__name__} executes only on CUDA tensors through liby5b200 (no CPU/PyTorch fallback)"
             )
-        if self.training:
-            raise NotImplementedError("y5b200: training-mode (batch-statistics BatchNorm) forward is not built yet")
+        if self.training:  # batch-statistics BatchNorm + autograd: yolov5_b200/train_ops.py
+            from ..train_ops import _run, train_dtype
+
+            dt = train_dtype(self)
+            with torch.autocast("cuda", enabled=False):
+                return _run(self, x.to(dt), dt)
         key = (tuple(x.shape), x.dtype, x.device.index, _param_version(self))
         cache = self.__dict__.setdefault("_y5_programs", {})
         prog = cache.get(key)

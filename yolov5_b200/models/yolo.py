@@ -4,7 +4,8 @@ inplace``, ``Detect`` / ``Segment`` with ``nc no nl na anchors m stride``, and i
 
 Differences that follow from being an engine rather than a torch.nn graph:
   * strides are derived from the layer table instead of a 256x256 probe forward (models/yolo.py:250-256);
-  * ``forward`` accepts CUDA tensors only and runs a cached engine Program per (batch, H, W, dtype);
+  * ``forward`` accepts CUDA tensors only and runs a cached engine Program per (batch, H, W, dtype); in training mode
+    (``model.train()``) it runs yolov5_b200.train_ops.forward_train instead (batch-statistics BN, autograd);
   * eval forward returns ``(z, [raw_i])`` / Segment ``(z, proto, [raw_i])`` exactly like models/yolo.py:115,150.
 """
 from __future__ import annotations
@@ -154,14 +155,16 @@ class BaseModel(nn.Module):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise RuntimeError("y5b200: the engine executes on CUDA tensors only (no CPU / PyTorch fallback); "
                                "move the model and the input to a B200")
-        if self.training:
-            raise NotImplementedError("y5b200: training-mode forward (batch-statistics BatchNorm + autograd) is not built yet")
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"y5b200: expected a (B,3,H,W) image batch, got {tuple(x.shape)}")
         head = self.model[-1]
         gs = int(max(self.stride)) if getattr(self, "stride", None) is not None else 32
         if x.shape[2] % gs or x.shape[3] % gs:
             raise ValueError(f"y5b200: image size {tuple(x.shape[2:])} must be a multiple of the max stride {gs}")
+        if self.training:  # list of raw (B,na,ny,nx,no) maps with an autograd graph, as models/yolo.py:98 returns
+            from ..train_ops import forward_train
+
+            return forward_train(self, x)
         z, raws, proto = self._program(x).run_model(x)
         if isinstance(head, Segment):
             return (z, proto) if head.export else (z, proto, raws)

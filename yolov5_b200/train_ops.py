@@ -1,0 +1,358 @@
+"""Training-mode execution of the hot path: Conv = SiLU(BN_batchstats(conv(x))) forward and backward on liby5b200.
+
+Reference: models/common.py:86-88 (Conv.forward), :181 (Bottleneck), :246 (C3), :338-340 (SPPF), :453 (Concat),
+models/yolo.py:95-98 (Detect in training returns the raw (B,na,ny,nx,no) maps), :160-170 (_forward_once routing);
+train.py:401-410 (autocast forward, scaled backward).
+
+What runs where
+  * every convolution (forward, data gradient, weight gradient), BatchNorm batch statistics / normalise / backward and
+    SiLU forward / backward: liby5b200 kernels (tcgen05 implicit GEMMs + HBM-bound passes), wrapped in
+    torch.autograd.Function so gradients land in the ordinary ``.grad`` of the nn.Parameters (DDP's bucketed NCCL
+    all-reduce -- smart_DDP -- works unchanged);
+  * the data-movement glue between convolutions (channel concat, 2x nearest upsample, 5x5 max-pool, residual add) is
+    left to torch autograd in this first training path.  Activations are channels_last, so those ops read and write
+    the same NHWC bytes the kernels use and no layout conversion happens anywhere.
+
+Precision: activations and their gradients in fp16/bf16 (the autocast dtype, or the parameter dtype if the model was
+cast), BN statistics / affine gradients / weight gradients in fp32 -- the reference's AMP recipe.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import ConvDesc, WgradDesc
+from .engine import pack_weight, stem_weight_s2d
+
+_CL = torch.channels_last
+
+
+def _st(dev):
+    return C.c_void_p(_lib.stream_ptr(dev))
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    """dense channels_last (NHWC bytes) view / copy of a (B,C,H,W) tensor"""
+    b, c, h, w = x.shape
+    if x.stride() == (h * w * c, 1, w * c, c):
+        return x
+    y = torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=x.dtype, device=x.device)
+    y.copy_(x)
+    return y
+
+
+def _empty_cl(b, c, h, w, dtype, device):
+    return torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=dtype, device=device)
+
+
+_zero_bias_cache: dict = {}
+
+
+def _zero_bias(n: int, device) -> torch.Tensor:
+    key = (n, str(device))
+    t = _zero_bias_cache.get(key)
+    if t is None:
+        t = _zero_bias_cache[key] = torch.zeros(n, dtype=torch.float32, device=device)
+    return t
+
+
+def conv_raw(x: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor | None, k: int, s: int, p: int, act: bool = False) -> torch.Tensor:
+    """y = act(conv(x, w) + bias) through y5_conv_bn_silu_fwd.  x: (B,Cin,H,W) channels_last fp16/bf16; w fp32/any OIHW."""
+    lib = _lib.lib()
+    b, cin, h, w = x.shape
+    cout = w_oihw.shape[0]
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    if cin % 8 or cout % 8:
+        raise NotImplementedError(f"y5b200: training convs need channel counts that are multiples of 8 (got {cin} -> {cout})")
+    bk, bn = C.c_int32(), C.c_int32()
+    _lib.check(lib.y5_conv_pick(cin, cout, b * ho * wo, C.byref(bk), C.byref(bn)), "conv_pick")
+    wp = pack_weight(w_oihw.detach(), bk.value, x.dtype)
+    bias32 = _zero_bias(cout, x.device) if bias is None else bias.detach().float().contiguous()
+    y = _empty_cl(b, cout, ho, wo, x.dtype, x.device)
+    d = ConvDesc()
+    d.inp, d.in_pitch = x.data_ptr(), cin
+    d.batch, d.in_h, d.in_w, d.in_c = b, h, w, cin
+    d.weight, d.bias = wp.data_ptr(), bias32.data_ptr()
+    d.out, d.out_pitch, d.out_c = y.data_ptr(), cout, cout
+    d.ksize, d.stride, d.pad = k, s, p
+    d.act = _lib.ACT_SILU if act else _lib.ACT_NONE
+    d.dtype, d.block_k, d.block_n = _lib.dtype_code(x.dtype), bk.value, 0
+    _lib.check(lib.y5_conv_bn_silu_fwd(C.byref(d), _st(x.device)), "conv fprop/dgrad")
+    return y
+
+
+def conv_dgrad(dy: torch.Tensor, w_oihw: torch.Tensor, k: int, s: int, p: int, in_hw: tuple[int, int]) -> torch.Tensor:
+    """dx of y = conv(x, w): a stride-1 conv of dy with the flipped, transposed filter (stride-2 layers first expand dy
+    with zeros).  dy: (B,Cout,Ho,Wo) channels_last."""
+    lib = _lib.lib()
+    b, cout, ho, wo = dy.shape
+    if s == 2:
+        if in_hw != (2 * ho, 2 * wo):
+            raise NotImplementedError("y5b200: stride-2 data gradient needs even input height/width")
+        z = _empty_cl(b, cout, 2 * ho, 2 * wo, dy.dtype, dy.device)
+        _lib.check(lib.y5_zero_stuff2x(dy.data_ptr(), cout, z.data_ptr(), cout, b, ho, wo, cout, _lib.dtype_code(dy.dtype), _st(dy.device)),
+                   "zero_stuff2x")
+        dy = z
+    elif s != 1:
+        raise NotImplementedError(f"y5b200: conv stride {s} backward")
+    wt = w_oihw.detach().flip(2, 3).transpose(0, 1)  # (Cin, Cout, k, k)
+    dx = conv_raw(dy, wt, None, k, 1, k - 1 - p, act=False)
+    assert tuple(dx.shape[2:]) == tuple(in_hw), (dx.shape, in_hw)
+    return dx
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, s: int, p: int) -> torch.Tensor:
+    """fp32 dW (Cout,Cin,k,k) of y = conv(x, w) from channels_last x and dy."""
+    lib = _lib.lib()
+    b, cin, h, w = x.shape
+    cout = dy.shape[1]
+    dw = torch.empty(cout, k, k, cin, dtype=torch.float32, device=x.device)
+    d = WgradDesc()
+    d.inp, d.in_pitch = x.data_ptr(), cin
+    d.batch, d.in_h, d.in_w, d.in_c = b, h, w, cin
+    d.dout, d.dout_pitch, d.out_c = dy.data_ptr(), cout, cout
+    d.dweight = dw.data_ptr()
+    d.ksize, d.stride, d.pad = k, s, p
+    d.dtype, d.accumulate = _lib.dtype_code(x.dtype), 0
+    _lib.check(lib.y5_conv_wgrad(C.byref(d), _st(x.device)), "conv_wgrad")
+    return dw.permute(0, 3, 1, 2)
+
+
+def _bn_ws(c: int, device) -> torch.Tensor:
+    return torch.empty(2 * c, dtype=torch.float64, device=device)
+
+
+class _ConvBnAct(torch.autograd.Function):
+    """z = act(BN(conv(x, w)))  with batch statistics (training) or running statistics (eval inside a training graph)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, k, s, p, act, eps, momentum, training, stem):
+        lib = _lib.lib()
+        dev = x.device
+        if stem:  # x is already the 16-channel space-to-depth image; weight is the (O,3,6,6) stem filter
+            w_eff, ke, se, pe = stem_weight_s2d(weight.detach().float()), 3, 1, 1
+        else:
+            w_eff, ke, se, pe = weight, k, s, p
+        x = _cl(x)
+        y = conv_raw(x, w_eff, None, ke, se, pe, act=False)
+        b, c, ho, wo = y.shape
+        rows = b * ho * wo
+        code = _lib.dtype_code(y.dtype)
+        if training:
+            mean = torch.empty(c, dtype=torch.float32, device=dev)
+            invstd = torch.empty(c, dtype=torch.float32, device=dev)
+            ws = _bn_ws(c, dev)
+            # the kernel updates fp32 running statistics in place; a model cast to fp16/bf16 goes through fp32 copies
+            rm = running_mean if running_mean is None or running_mean.dtype == torch.float32 else running_mean.float()
+            rv = running_var if running_var is None or running_var.dtype == torch.float32 else running_var.float()
+            _lib.check(lib.y5_bn_stats(y.data_ptr(), c, rows, c, code, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
+                                       rm.data_ptr() if rm is not None else None, rv.data_ptr() if rv is not None else None,
+                                       ws.data_ptr(), _st(dev)), "bn_stats")
+            if rm is not running_mean:
+                running_mean.copy_(rm)
+            if rv is not running_var:
+                running_var.copy_(rv)
+        else:
+            mean = running_mean.float()
+            invstd = torch.rsqrt(running_var.float() + eps)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        z = torch.empty_like(y)
+        _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(),
+                                     b32.data_ptr(), 1 if act else 0, _st(dev)), "bn_act_fwd")
+        ctx.save_for_backward(x, weight, y, mean, invstd, g32, b32)
+        ctx.cfg = (k, s, p, act, training, stem, ke, se, pe)
+        ctx.pdtypes = (gamma.dtype, beta.dtype)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.lib()
+        x, weight, y, mean, invstd, g32, b32 = ctx.saved_tensors
+        k, s, p, act, training, stem, ke, se, pe = ctx.cfg
+        if not training:
+            raise NotImplementedError("y5b200: backward through eval-mode BatchNorm")
+        dev = y.device
+        b, c, ho, wo = y.shape
+        rows = b * ho * wo
+        code = _lib.dtype_code(y.dtype)
+        dz = _cl(dz.to(y.dtype))
+        dy = torch.empty_like(y)
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        ws = _bn_ws(c, dev)
+        _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), c, dy.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
+                                     g32.data_ptr(), b32.data_ptr(), 1 if act else 0, dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
+                                     _st(dev)), "bn_act_bwd")
+        dw = conv_wgrad(x, dy, ke, se, pe)
+        if stem:  # (O,16,3,3) gradient of the space-to-depth filter -> (O,3,6,6)
+            full = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
+            for ddy in range(2):
+                for ddx in range(2):
+                    for ch in range(3):
+                        full[:, ch, ddy::2, ddx::2] = dw[:, (ddy * 2 + ddx) * 3 + ch]
+            dw = full
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if stem:
+                raise NotImplementedError("y5b200: gradient w.r.t. the input image")
+            dx = conv_dgrad(dy, weight, k, s, p, (x.shape[2], x.shape[3]))
+        return (dx, dw.to(weight.dtype), dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, None, None, None, None, None, None, None,
+                None)
+
+
+class _ConvBias(torch.autograd.Function):
+    """Detect.m[i]: 1x1 conv with bias, output channels padded to a multiple of 8; returns NHWC (B,H,W,Cpad)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _cl(x)
+        cout = weight.shape[0]
+        cpad = (cout + 7) // 8 * 8
+        wpad = torch.zeros(cpad, *weight.shape[1:], dtype=torch.float32, device=x.device)
+        wpad[:cout] = weight.detach().float()
+        bpad = torch.zeros(cpad, dtype=torch.float32, device=x.device)
+        bpad[:cout] = bias.detach().float()
+        y = conv_raw(x, wpad, bpad, 1, 1, 0, act=False)  # (B,cpad,H,W) channels_last
+        ctx.save_for_backward(x, wpad)
+        ctx.cout = cout
+        ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
+        return y.permute(0, 2, 3, 1)  # NHWC view, dense
+
+    @staticmethod
+    def backward(ctx, dy_nhwc):
+        lib = _lib.lib()
+        x, wpad = ctx.saved_tensors
+        cout = ctx.cout
+        dy = _cl(dy_nhwc.to(x.dtype).permute(0, 3, 1, 2))
+        b, cpad, h, w = dy.shape
+        dev = x.device
+        db = torch.empty(cpad, dtype=torch.float32, device=dev)
+        ws = _bn_ws(cpad, dev)
+        _lib.check(lib.y5_col_sum(dy.data_ptr(), cpad, b * h * w, cpad, _lib.dtype_code(dy.dtype), db.data_ptr(), ws.data_ptr(), _st(dev)),
+                   "col_sum")
+        dw = conv_wgrad(x, dy, 1, 1, 0)[:cout]
+        dx = conv_dgrad(dy, wpad, 1, 1, 0, (h, w)) if ctx.needs_input_grad[0] else None
+        return dx, dw.to(ctx.wdtype), db[:cout].to(ctx.bdtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# module-level training forward
+# ---------------------------------------------------------------------------------------------------------------------
+def train_dtype(model) -> torch.dtype:
+    """Activation dtype of the training forward: the autocast dtype when autocast is on (train.py:401), else the
+    parameter dtype if the model was cast to fp16/bf16."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+    else:
+        dt = next(model.parameters()).dtype
+    if dt not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("y5b200: the training forward computes in fp16/bf16 with fp32 statistics and weight gradients -- run it under "
+                           "torch.autocast('cuda') (as reference train.py:401 does) or cast the model with .half()/.bfloat16()")
+    return dt
+
+
+def conv_module(m, x, stem: bool = False):
+    bn = getattr(m, "bn", None)
+    if bn is None:
+        raise RuntimeError("y5b200: cannot train a fused model (Conv without BatchNorm); build it unfused")
+    act = isinstance(m.act, torch.nn.SiLU)
+    if not act and not isinstance(m.act, torch.nn.Identity):
+        raise NotImplementedError(f"y5b200: activation {type(m.act).__name__}")
+    if m.conv.groups != 1 or m.conv.dilation[0] != 1:
+        raise NotImplementedError("y5b200: grouped / dilated convolutions are outside the YOLOv5 n..x hot path")
+    k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
+    if not stem and (k, s, p) not in ((1, 1, 0), (3, 1, 1), (3, 2, 1)):
+        raise NotImplementedError(f"y5b200: training conv k{k} s{s} p{p}")
+    training = bn.training
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    return _ConvBnAct.apply(x, m.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s, p, act, float(bn.eps), float(mom),
+                            training, stem)
+
+
+def stem_input(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(B,3,H,W) uint8 / float image -> (B,16,H/2,W/2) channels_last space-to-depth tensor (12 channels used)."""
+    lib = _lib.lib()
+    b, c, h, w = img.shape
+    if c != 3 or h % 2 or w % 2:
+        raise ValueError(f"y5b200: expected a (B,3,even,even) image batch, got {tuple(img.shape)}")
+    img = img.contiguous()
+    out = _empty_cl(b, 16, h // 2, w // 2, dtype, img.device)
+    _lib.check(lib.y5_stem_s2d(img.data_ptr(), _lib.dtype_code(img.dtype), out.data_ptr(), _lib.dtype_code(dtype), b, h, w, w // 2, 0,
+                               _st(img.device)), "stem_s2d")
+    return out
+
+
+def _run(m, x, dt):
+    from .models import common as mc
+    from .models import yolo as my
+
+    if isinstance(m, mc.Conv):
+        return conv_module(m, x)
+    if isinstance(m, mc.Bottleneck):
+        y = conv_module(m.cv2, conv_module(m.cv1, x))
+        return x + y if m.add else y
+    if isinstance(m, mc.C3):
+        a = conv_module(m.cv1, x)
+        for bt in m.m:
+            a = _run(bt, a, dt)
+        return conv_module(m.cv3, torch.cat((a, conv_module(m.cv2, x)), 1))
+    if isinstance(m, mc.SPPF):
+        a = conv_module(m.cv1, x)
+        k = m.m.kernel_size if isinstance(m.m.kernel_size, int) else m.m.kernel_size[0]
+        y1 = F.max_pool2d(a, k, 1, k // 2)
+        y2 = F.max_pool2d(y1, k, 1, k // 2)
+        y3 = F.max_pool2d(y2, k, 1, k // 2)
+        return conv_module(m.cv2, torch.cat((a, y1, y2, y3), 1))
+    if isinstance(m, torch.nn.Upsample):
+        return F.interpolate(x, scale_factor=m.scale_factor, mode=m.mode)
+    if isinstance(m, mc.Concat):
+        return torch.cat(x, m.d)
+    if isinstance(m, mc.Proto):
+        a = conv_module(m.cv1, x)
+        a = F.interpolate(a, scale_factor=2.0, mode="nearest")
+        return conv_module(m.cv3, conv_module(m.cv2, a))
+    if isinstance(m, torch.nn.Sequential):
+        for sub in m:
+            x = _run(sub, x, dt)
+        return x
+    if isinstance(m, my.Detect):
+        outs = []
+        for i, xi in enumerate(x):
+            yi = _ConvBias.apply(xi, m.m[i].weight, m.m[i].bias)  # (B,ny,nx,cpad)
+            b, ny, nx, _ = yi.shape
+            outs.append(yi[..., : m.na * m.no].reshape(b, ny, nx, m.na, m.no).permute(0, 3, 1, 2, 4).contiguous())
+        if isinstance(m, my.Segment):
+            return outs, _run(m.proto, x[0], dt)
+        return outs
+    raise NotImplementedError(f"y5b200: module {type(m).__name__} is outside the engine's hot path")
+
+
+def forward_train(model, img: torch.Tensor):
+    """Training-mode DetectionModel / SegmentationModel forward: list of raw (B,na,ny,nx,no) maps (Segment: (list, proto)),
+    differentiable w.r.t. every parameter."""
+    from .models import common as mc
+
+    dt = train_dtype(model)
+    layers = list(model.model)
+    first = layers[0]
+    if not (isinstance(first, mc.Conv) and first.conv.kernel_size[0] == 6 and first.conv.stride[0] == 2 and first.conv.padding[0] == 2
+            and first.conv.in_channels == 3):
+        raise NotImplementedError("y5b200: the first layer must be the YOLOv5 v6 stem Conv(3, c, 6, 2, 2)")
+    ys = []
+    x = None
+    # every op below picks its dtype explicitly; autocast's own casting rules must not touch the glue ops
+    with torch.autocast("cuda", enabled=False):
+        for i, m in enumerate(layers):
+            if i == 0:
+                x = conv_module(m, stem_input(img, dt), stem=True)
+            else:
+                if m.f != -1:
+                    x = ys[m.f] if isinstance(m.f, int) else [x if j == -1 else ys[j] for j in m.f]
+                x = _run(m, x, dt)
+            ys.append(x if i in model.save else None)
+    return x
