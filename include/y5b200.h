@@ -206,8 +206,8 @@ int y5_loss_read_targets(const y5_loss_params* p, const void* workspace, int32_t
 /* ------------------------------------------------------------------------------------------------------------------
  * Training-mode Conv = SiLU(BN(conv(x)))  (reference models/common.py:86-88; gradients of the same).
  * Forward:   y = conv(x, W)            -> y5_conv_bn_silu_fwd with act = Y5_ACT_NONE and a zero bias (same kernel)
- *            mean/invstd = stats(y)    -> y5_bn_stats      (also updates running_mean / running_var, momentum 0.03)
- *            z = act(bn(y))            -> y5_bn_act_fwd
+ *            column sums of y          -> y5_bn_stats
+ *            z = act(bn(y))            -> y5_bn_act_fwd    (derives mean/invstd, updates running_mean / running_var)
  * Backward:  dy, dgamma, dbeta         -> y5_bn_act_bwd
  *            dW                        -> y5_conv_wgrad    (tcgen05, MN-major operands straight from NHWC)
  *            dx = conv(dy, W^T flipped)-> y5_conv_bn_silu_fwd again on transposed/flipped packed weights (stride-2
@@ -229,16 +229,20 @@ typedef struct y5_wgrad_desc {
 } y5_wgrad_desc;
 int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream);
 
-/* workspace for y5_bn_stats / y5_bn_act_bwd / y5_col_sum: 2 * channels doubles */
+/* workspace of y5_bn_stats / y5_bn_act_bwd / y5_col_sum: 2 * channels doubles.  For y5_bn_stats and y5_bn_act_bwd it
+ * must be ZERO on entry and is left dirty (callers carve it from one arena cleared once per step); y5_col_sum clears
+ * its own. */
 int64_t y5_bn_workspace_bytes(int32_t channels);
-/* per-channel batch mean and 1/sqrt(biased var + eps) of a [rows][channels] view; running stats (nullable) updated as
- * nn.BatchNorm2d does (unbiased variance). */
-int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, float eps, float momentum,
-                float* mean, float* invstd, float* running_mean, float* running_var, void* workspace, void* stream);
-/* z = act(gamma * (y - mean) * invstd + beta), act: Y5_ACT_NONE | Y5_ACT_SILU; z may be a channel-slice view */
+/* per-channel sum and sum of squares of a [rows][channels] view, accumulated into workspace (fp64) */
+int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, void* workspace,
+                void* stream);
+/* z = act(gamma * (y - mean) * invstd + beta), act: Y5_ACT_NONE | Y5_ACT_SILU; z may be a channel-slice view.
+ * sums != NULL (training): mean / invstd (biased variance + eps) are first derived from the y5_bn_stats workspace and
+ * WRITTEN to mean / invstd, and running_mean / running_var (nullable) are updated like nn.BatchNorm2d does (momentum,
+ * unbiased variance).  sums == NULL (eval): mean / invstd are inputs. */
 int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int64_t rows, int32_t channels,
-                  int32_t dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                  int32_t act, void* stream);
+                  int32_t dtype, float* mean, float* invstd, const float* gamma, const float* beta, int32_t act,
+                  const void* sums, float eps, float momentum, float* running_mean, float* running_var, void* stream);
 /* given dz: dy (gradient w.r.t. the conv output), dgamma, dbeta (fp32, overwritten) */
 int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* dz, int32_t dz_pitch, void* dy, int32_t dy_pitch,
                   int64_t rows, int32_t channels, int32_t dtype, const float* mean, const float* invstd,
@@ -247,6 +251,11 @@ int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* dz, int32_t dz_pit
 /* out[c] = sum over rows of y[row][c] (fp32) */
 int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, float* out, void* workspace,
                void* stream);
+/* OIHW master weights (Y5_F32 | Y5_F16 | Y5_BF16) -> K-major packings in `dtype` for y5_conv_bn_silu_fwd, either may be
+ * NULL:  fwd [out_c][k][k][in_c_pad] = w[o][i][r][s]  and  dgrad [in_c][k][k][out_c_pad] = w[o][i][k-1-r][k-1-s]
+ * (padding channels zero; pads = channel counts rounded up to the block_k y5_conv_pick returns). */
+int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t ksize, void* fwd, int32_t in_c_pad,
+                   void* dgrad, int32_t out_c_pad, int32_t dtype, void* stream);
 /* y[n, 2i, 2j, :] = x[n, i, j, :], other pixels of the (2h, 2w) output zero */
 int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int32_t batch, int32_t h, int32_t w,
                     int32_t c, int32_t dtype, void* stream);

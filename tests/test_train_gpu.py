@@ -77,9 +77,11 @@ def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
     beta = (torch.rand(C_, generator=g) - 0.5).to(cuda)
     rm, rv = torch.zeros(C_, device=cuda), torch.ones(C_, device=cuda)
     mean, invstd = torch.empty(C_, device=cuda), torch.empty(C_, device=cuda)
-    ws = torch.empty(2 * C_, dtype=torch.float64, device=cuda)
-    _lib.check(lib.y5_bn_stats(y.data_ptr(), C_, rows, C_, code, 1e-3, 0.03, mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(), rv.data_ptr(),
-                               ws.data_ptr(), st))
+    ws = torch.zeros(2 * C_, dtype=torch.float64, device=cuda)  # zero on entry
+    z = torch.empty_like(y)
+    _lib.check(lib.y5_bn_stats(y.data_ptr(), C_, rows, C_, code, ws.data_ptr(), st))
+    _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                 beta.data_ptr(), 1, ws.data_ptr(), 1e-3, 0.03, rm.data_ptr(), rv.data_ptr(), st))
     yd = y.double().permute(0, 2, 3, 1).reshape(rows, C_)
     m_ref, v_ref = yd.mean(0), yd.var(0, unbiased=False)
     assert torch.allclose(mean.double(), m_ref, rtol=1e-5, atol=1e-6)
@@ -87,9 +89,11 @@ def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
     assert torch.allclose(rm.double(), 0.03 * m_ref, rtol=1e-5, atol=1e-7)
     assert torch.allclose(rv.double(), 0.97 + 0.03 * yd.var(0, unbiased=True), rtol=1e-5)
     # forward: same rounding points as torch autocast (BN result rounded, SiLU of the rounded value)
-    z = torch.empty_like(y)
-    _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                 beta.data_ptr(), 1, st))
+    # eval form (statistics given) must produce the same output
+    z2 = torch.empty_like(y)
+    _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z2.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                 beta.data_ptr(), 1, None, 1e-3, 0.03, None, None, st))
+    assert torch.equal(z, z2)
     u = ((y.float() - mean.view(1, -1, 1, 1)) * (invstd * gamma).view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)).to(dtype)
     z_ref = F.silu(u.float()).to(dtype)
     ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
@@ -98,6 +102,7 @@ def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
     dz = _cl_rand((B, C_, H, W), dtype, cuda, 7)
     dy = torch.empty_like(y)
     dg, db = torch.empty(C_, device=cuda), torch.empty(C_, device=cuda)
+    ws.zero_()
     _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), C_, dz.data_ptr(), C_, dy.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(),
                                  gamma.data_ptr(), beta.data_ptr(), 1, dg.data_ptr(), db.data_ptr(), ws.data_ptr(), st))
     yf = y.float().requires_grad_(True)

@@ -6,12 +6,16 @@
 // canonical MN-major SW128 layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- each pixel is one 128-byte line
 // of 64 channels, 8 pixels form a 1024-byte swizzle atom (SBO), further 64-channel blocks sit LBO bytes apart.  So
 // neither dY nor X is ever transposed in memory; the tensor core does it on the fly.
-//   A (dY)   : 2 boxes [64 px][64 co] per stage  -> UMMA M = 128 output channels
-//   B (X_tap): n boxes [64 px][64 ci] per stage  -> UMMA N = 64*n input channels (n <= 4); hardware im2col for k > 1 or
-//              strided convs (same tensor map type as the forward kernel), plain 2-D tiles for 1x1/s1
-// One CTA = one (co tile, tap, ci tile, pixel range) work item: it streams its pixel range through a 4-stage TMA ring,
-// accumulates the [128 x 64n] fp32 tile in TMEM and adds it to the fp32 gradient with vector reductions
-// (red.global.add.v4.f32): the pixel range is split so the grid covers the machine about twice.
+//   A (dY)   : 1-2 boxes [P px][64 co] per stage -> UMMA M = 128 output channels (the upper box is not fetched when the
+//              layer has <= 64 of them left: its accumulator rows are never read)
+//   B (X_tap): n boxes [P px][64 ci] per stage per tap -> UMMA N = 64*n input channels (n <= 4); hardware im2col for
+//              k > 1 or strided convs (same tensor map type as the forward kernel), plain 2-D tiles for 1x1/s1
+// One CTA = one (co tile, tap group, ci tile, pixel range) work item.  A tap group is up to G filter taps whose
+// accumulators sit side by side in TMEM (G * 64n <= 512 columns): the dY tile of a pixel block is fetched once and
+// multiplied with the G shifted X tiles, which divides the dY traffic of 3x3 layers by G.  P (64/128/256 pixels per
+// pipeline stage) grows when channels are few so that a stage stays ~32-64 KB and the per-stage barrier / TMA issue
+// costs are amortised.  The [128 x 64n] fp32 tiles are added to the fp32 gradient with vector reductions
+// (red.global.add.v4.f32); the pixel range is split so the grid is about one CTA per SM (one wave).
 // Summation order across pixel ranges is not fixed (fp32 atomics), like cuDNN's default wgrad.
 //
 // Gradient of reference models/common.py:86-88 (Conv.forward, the nn.Conv2d weight) / models/yolo.py:97 (Detect.m[i]).
@@ -26,10 +30,8 @@
 namespace y5 {
 
 constexpr int kWgThreads = 64 + 128;  // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
-constexpr int kWgPix = 64;            // pixels (GEMM K) per pipeline stage
 constexpr int kWgCo = 128;            // output channels per tile (UMMA M)
 constexpr int kWgStagesMax = 6;
-constexpr uint32_t kWgBlockBytes = kWgPix * 128;  // one [64 px][64 ch] box
 
 struct WgradParams {
     int M, Cout, Cin;
@@ -37,9 +39,11 @@ struct WgradParams {
     int linear;                 // 1x1 / stride 1 / no padding: X tiles are plain 2-D boxes of the [M, Cin] matrix
     int n_blocks;               // 64-channel blocks of Cin per tile
     int ci_tiles, taps;
+    int group, tap_groups;      // taps per CTA, number of tap groups
+    int pix;                    // pixels (GEMM K) per pipeline stage: 64 | 128 | 256
     int kblocks, splits, kb_per_split;
     int stages;
-    uint32_t stage_bytes;
+    uint32_t box_bytes, stage_bytes;
     uint32_t idesc, tmem_cols;
     float* dw;
 };
@@ -79,21 +83,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     t /= p.splits;
     const int ci_tile = t % p.ci_tiles;
     t /= p.ci_tiles;
-    const int tap = t % p.taps;
-    const int co_tile = t / p.taps;
-    const int r = tap / p.kw, s = tap - r * p.kw;
+    const int tg = t % p.tap_groups;
+    const int co_tile = t / p.tap_groups;
+    const int tap0 = tg * p.group;
+    const int ntaps = min(p.group, p.taps - tap0);
     const int co0 = co_tile * kWgCo;
-    const int ci0 = ci_tile * p.n_blocks * 64;
+    const int a_boxes = p.Cout - co0 > 64 ? 2 : 1;
+    const int bn = p.n_blocks * 64;
+    const int ci0 = ci_tile * bn;
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
     const int nkb = kb1 - kb0;
+    // stage layout: [A box 0][A box 1][tap 0: n boxes][tap 1: n boxes]...
+    const uint32_t tx_bytes = (a_boxes + ntaps * p.n_blocks) * p.box_bytes;
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         int st = 0;
         uint32_t ph = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int m0 = kb * kWgPix;
+            const int m0 = kb * p.pix;
             int img = 0, y0 = 0, x0 = 0;
             if (!p.linear) {
                 img = m0 / p.HoWo;
@@ -105,15 +114,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
             mbar_wait(&empty[st], ph ^ 1);
             if (elect_one()) {
                 uint8_t* dst = ring + st * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[st], p.stage_bytes);
+                mbar_arrive_expect_tx(&full[st], tx_bytes);
                 tma_load_2d(&tmDy, &full[st], dst, co0, m0);
-                tma_load_2d(&tmDy, &full[st], dst + kWgBlockBytes, co0 + 64, m0);
-                for (int j = 0; j < p.n_blocks; ++j) {
-                    uint8_t* b_dst = dst + (2 + j) * kWgBlockBytes;
-                    if (p.linear) tma_load_2d(&tmX, &full[st], b_dst, ci0 + j * 64, m0);
-                    else
-                        tma_load_im2col_4d(&tmX, &full[st], b_dst, ci0 + j * 64, x0, y0, img, static_cast<uint16_t>(s),
-                                           static_cast<uint16_t>(r));
+                if (a_boxes == 2) tma_load_2d(&tmDy, &full[st], dst + p.box_bytes, co0 + 64, m0);
+                for (int g = 0; g < ntaps; ++g) {
+                    const int tap = tap0 + g;
+                    const int r = tap / p.kw, s = tap - r * p.kw;
+                    for (int j = 0; j < p.n_blocks; ++j) {
+                        uint8_t* b_dst = dst + (2 + g * p.n_blocks + j) * p.box_bytes;
+                        if (p.linear) tma_load_2d(&tmX, &full[st], b_dst, ci0 + j * 64, m0);
+                        else
+                            tma_load_im2col_4d(&tmX, &full[st], b_dst, ci0 + j * 64, x0, y0, img, static_cast<uint16_t>(s),
+                                               static_cast<uint16_t>(r));
+                    }
                 }
             }
             __syncwarp();
@@ -123,21 +136,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         // ===================================== MMA issuer =====================================
         int st = 0;
         uint32_t ph = 0;
-        // MN-major SW128 descriptors: SBO = 1024 B between 8-pixel groups, LBO = one [64 px][64 ch] box between
+        // MN-major SW128 descriptors: SBO = 1024 B between 8-pixel groups, LBO = one [P px][64 ch] box between
         // 64-channel blocks; stepping 16 pixels along K = +2048 B on the start address
         const uint32_t dhi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
-        const uint32_t lbo = ((kWgBlockBytes >> 4) & 0x3FFFu) << 16;
+        const uint32_t lbo = ((p.box_bytes >> 4) & 0x3FFFu) << 16;
         const uint32_t ring16 = (smem_u32(ring) >> 4) & 0x3FFFu;
+        const uint32_t box16 = p.box_bytes >> 4;
+        const int ksteps = p.pix / 16;
         uint32_t accum = 0;
         for (int i = 0; i < nkb; ++i) {
             mbar_wait(&full[st], ph);
             tc_fence_after();
             const uint32_t a16 = ring16 + ((st * p.stage_bytes) >> 4);
-            const uint32_t b16 = a16 + ((2 * kWgBlockBytes) >> 4);
             if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < kWgPix / 16; ++k)
-                    umma_f16_ss_lohi(tmem_base, (a16 + k * 128) | lbo, (b16 + k * 128) | lbo, dhi, p.idesc, (accum | k) != 0 ? 1u : 0u);
+                for (int g = 0; g < ntaps; ++g) {
+                    const uint32_t b16 = a16 + (2 + g * p.n_blocks) * box16;
+                    const uint32_t d = tmem_base + g * bn;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_f16_ss_lohi(d, (a16 + k * 128) | lbo, (b16 + k * 128) | lbo, dhi, p.idesc, (accum | k) != 0 ? 1u : 0u);
+                }
                 umma_commit(&empty[st]);
                 if (i == nkb - 1) umma_commit(acc_full);
             }
@@ -152,27 +169,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         tc_fence_after();
         const int co = co0 + q * 32 + lane;
         const bool row_ok = co < p.Cout;
-        float* row = p.dw + (static_cast<size_t>(row_ok ? co : 0) * p.taps + tap) * p.Cin;
         const bool vec_ok = (p.Cin & 3) == 0;
-        for (int c = 0; c < p.n_blocks * 2; ++c) {
-            const int cbase = ci0 + c * 32;
-            if (cbase >= p.Cin) break;  // warp-uniform
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-            tmem_ld_wait();
-            if (row_ok) {
+        for (int g = 0; g < ntaps; ++g) {
+            float* row = p.dw + (static_cast<size_t>(row_ok ? co : 0) * p.taps + tap0 + g) * p.Cin;
+            for (int c = 0; c < p.n_blocks * 2; ++c) {
+                const int cbase = ci0 + c * 32;
+                if (cbase >= p.Cin) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * bn + c * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ci = cbase + 4 * j;
-                    if (vec_ok && ci + 3 < p.Cin) {
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci), "f"(__uint_as_float(v[4 * j])),
-                                     "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
-                                     "f"(__uint_as_float(v[4 * j + 3]))
-                                     : "memory");
-                    } else {
+                    for (int j = 0; j < 8; ++j) {
+                        const int ci = cbase + 4 * j;
+                        if (vec_ok && ci + 3 < p.Cin) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci), "f"(__uint_as_float(v[4 * j])),
+                                         "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])),
+                                         "f"(__uint_as_float(v[4 * j + 3]))
+                                         : "memory");
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (ci + e < p.Cin) atomicAdd(row + ci + e, __uint_as_float(v[4 * j + e]));
+                            for (int e = 0; e < 4; ++e)
+                                if (ci + e < p.Cin) atomicAdd(row + ci + e, __uint_as_float(v[4 * j + e]));
+                        }
                     }
                 }
             }
@@ -223,39 +242,53 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
     // balance the blocks over the ci tiles (e.g. 5 blocks -> 3 + 2, not 4 + 1)
     p.n_blocks = (blocks_total + p.ci_tiles - 1) / p.ci_tiles;
     const int co_tiles = (d->out_c + kWgCo - 1) / kWgCo;
-    p.kblocks = (p.M + kWgPix - 1) / kWgPix;
-    const long long items = static_cast<long long>(co_tiles) * p.taps * p.ci_tiles;
-    long long want = (2LL * sm_count() + items - 1) / items;  // pixel ranges per tile so the grid covers the machine ~twice
+    const int bn = p.n_blocks * 64;
+    // taps per CTA: accumulators of a group share TMEM (512 columns); a 256-wide tile keeps one tap (its stage is
+    // already 48 KB); groups are balanced (9 taps, limit 5 -> 5 + 4)
+    int gmax = bn >= 256 ? 1 : 512 / bn;
+    if (gmax > 5) gmax = 5;
+    p.tap_groups = (p.taps + gmax - 1) / gmax;
+    p.group = (p.taps + p.tap_groups - 1) / p.tap_groups;
+    // pixels per stage: as many as keep a stage within ~56 KB (>= 3 stages in flight)
+    p.pix = 64;
+    for (int cand : {256, 128}) {
+        if (static_cast<uint32_t>(2 + p.group * p.n_blocks) * cand * 128u <= 56u * 1024u) { p.pix = cand; break; }
+    }
+    p.box_bytes = p.pix * 128u;
+    p.kblocks = (p.M + p.pix - 1) / p.pix;
+    const long long items = static_cast<long long>(co_tiles) * p.tap_groups * p.ci_tiles;
+    long long want = (sm_count() + items - 1) / items;  // pixel ranges per tile: one CTA per SM, one wave
     if (want < 1) want = 1;
     if (want > p.kblocks) want = p.kblocks;
     p.kb_per_split = static_cast<int>((p.kblocks + want - 1) / want);
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty range
-    p.stage_bytes = (2 + p.n_blocks) * kWgBlockBytes;
+    p.stage_bytes = (2 + p.group * p.n_blocks) * p.box_bytes;
     p.stages = static_cast<int>((200u * 1024u) / p.stage_bytes);
     if (p.stages > kWgStagesMax) p.stages = kWgStagesMax;
-    const int bn = p.n_blocks * 64;
+    if (p.stages < 2) return set_error(Y5_E_UNSUPPORTED, "wgrad: stage does not fit shared memory");
     p.idesc = umma_idesc_f16(d->dtype == Y5_BF16, bn) | (1u << 15) | (1u << 16);  // A and B MN-major
-    p.tmem_cols = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+    const int cols = p.group * bn;
+    p.tmem_cols = cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512));
     p.dw = d->dweight;
 
     CUtensorMap tmDy, tmX;
     {
         cuuint64_t dims[2] = {(cuuint64_t)d->out_c, (cuuint64_t)M};
         cuuint64_t str[1] = {(cuuint64_t)d->dout_pitch * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)kWgPix};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.pix};
         int e = encode_tiled(&tmDy, d->dtype, d->dout, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad dY");
         if (e) return e;
     }
     if (p.linear) {
         cuuint64_t dims[2] = {(cuuint64_t)d->in_c, (cuuint64_t)M};
         cuuint64_t str[1] = {(cuuint64_t)d->in_pitch * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)kWgPix};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.pix};
         int e = encode_tiled(&tmX, d->dtype, d->in, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad X");
         if (e) return e;
     } else {
         const long long xs = d->in_pitch, ys = xs * d->in_w, ns = ys * d->in_h;
         int e = encode_im2col(&tmX, d->dtype, d->in, d->in_c, d->in_w, d->in_h, d->batch, xs, ys, ns, k, k, d->stride, d->pad, d->pad, 64,
-                              kWgPix, CU_TENSOR_MAP_SWIZZLE_128B);
+                              p.pix, CU_TENSOR_MAP_SWIZZLE_128B);
         if (e) return e;
     }
     const size_t dw_bytes = static_cast<size_t>(d->out_c) * p.taps * d->in_c * sizeof(float);

@@ -17,17 +17,24 @@
 namespace y5 {
 
 constexpr int kRedThreads = 256;
-constexpr int kRowsPerBlock = 1024;
 
 struct RowGeom {
     int cgx;   // channel groups (of 8) handled side by side by one block
     int rows;  // thread rows per block
+    int rpb;   // tensor rows per block: sized so the grid has ~8 blocks per SM (small maps) but at most 1024 rows
 };
-static inline RowGeom row_geom(int channels) {
+constexpr int kUnroll = 4;  // rows per loop trip of the statistics pass; the BN passes take 2 and rely on occupancy
+static inline RowGeom row_geom(int channels, long long nrows, int blocks_per_sm) {
     const int cg = channels / 8;
     RowGeom g;
     g.cgx = cg >= 32 ? 32 : (cg >= 16 ? 16 : (cg >= 8 ? 8 : (cg >= 4 ? 4 : (cg >= 2 ? 2 : 1))));
     g.rows = kRedThreads / g.cgx;
+    const long long gx = (cg + g.cgx - 1) / g.cgx;
+    const long long target = static_cast<long long>(sm_count()) * blocks_per_sm;
+    long long rpb = (nrows * gx + target - 1) / target;
+    const long long quantum = static_cast<long long>(g.rows) * kUnroll;
+    if (rpb < quantum) rpb = quantum;
+    g.rpb = static_cast<int>((rpb + quantum - 1) / quantum * quantum);
     return g;
 }
 
@@ -75,23 +82,32 @@ __device__ __forceinline__ void block_publish(float (&acc)[NV][8], int cgx, int 
 // mode 0: sum, sum of squares;  mode 1: sum only
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads) col_stats_kernel(const void* __restrict__ y, int pitch, long long rows, int channels, int bf16,
-                                                                int cgx, double* __restrict__ ws) {
+                                                                int cgx, int rpb, double* __restrict__ ws) {
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     const bool active = cg * 8 < channels;
     float acc[MODE == 0 ? 2 : 1][8] = {};
-    const long long r0 = static_cast<long long>(blockIdx.y) * kRowsPerBlock;
-    const long long r1 = min(rows, r0 + kRowsPerBlock);
+    const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
+    const long long r1 = min(rows, r0 + rpb);
     if (active)
-        for (long long r = r0 + ty; r < r1; r += nrows) {
-            float v[8];
-            load8(y, r * pitch + cg * 8, bf16 != 0, v);
+        for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
+            float v[kUnroll][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc[0][i] += v[i];
-                if (MODE == 0) acc[1][i] = fmaf(v[i], v[i], acc[1][i]);
+            for (int u = 0; u < kUnroll; ++u) {
+                const long long rr = r + u * nrows;
+                if (rr < r1) load8(y, rr * pitch + cg * 8, bf16 != 0, v[u]);
+                else
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
             }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[0][i] += v[u][i];
+                    if (MODE == 0) acc[1][i] = fmaf(v[u][i], v[u][i], acc[1][i]);
+                }
         }
     if constexpr (MODE == 0) {
         double* const dst[2] = {ws, ws + channels};
@@ -102,100 +118,136 @@ __global__ void __launch_bounds__(kRedThreads) col_stats_kernel(const void* __re
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ ws, long long rows, int channels, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= channels) return;
-    const double m = ws[c] / static_cast<double>(rows);
-    double var = ws[channels + c] / static_cast<double>(rows) - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[c] = static_cast<float>(m);
-    invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(m);
-    if (running_var) {
-        const double unbiased = rows > 1 ? var * static_cast<double>(rows) / static_cast<double>(rows - 1) : var;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-    }
-}
-
 __global__ void col_sum_finalize_kernel(const double* __restrict__ ws, int channels, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < channels) out[c] = static_cast<float>(ws[c]);
 }
 
-__global__ void __launch_bounds__(kRedThreads) bn_act_fwd_kernel(const void* __restrict__ y, int y_pitch, void* __restrict__ z, int z_pitch,
-                                                                 long long rows, int channels, int bf16, int act, int cgx,
-                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                 const float* __restrict__ gamma, const float* __restrict__ beta) {
-    const int nrows = kRedThreads / cgx;
-    const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
-    const int cg = blockIdx.x * cgx + tx;
-    if (cg * 8 >= channels) return;
-    float mu[8], sc[8], be[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = cg * 8 + i;
-        mu[i] = mean[c];
-        sc[i] = invstd[c] * gamma[c];
-        be[i] = beta[c];
-    }
-    const bool b = bf16 != 0;
-    const long long r0 = static_cast<long long>(blockIdx.y) * kRowsPerBlock;
-    const long long r1 = min(rows, r0 + kRowsPerBlock);
-    for (long long r = r0 + ty; r < r1; r += nrows) {
-        float v[8];
-        load8(y, r * y_pitch + cg * 8, b, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float u = round_lowp(fmaf(v[i] - mu[i], sc[i], be[i]), b);
-            v[i] = act ? u / (1.0f + expf(-u)) : u;
-        }
-        store8(z, r * z_pitch + cg * 8, b, v);
-    }
-}
+// Per-channel constants of the three passes live in shared memory (4 floats per channel of the block's channel groups):
+//   a = invstd*gamma, b = beta - mean*a           -> t = round(y*a + b) is the BN output
+//   forward : z = silu(t)
+//   reduce  : xh = y*is + m2 (m2 = -mean*invstd);  du = dz*silu'(t);  sum du, sum du*xh
+//   apply   : dy = du*a + y*c1 + c0  with c1 = -invstd*(dgamma/rows)*a,  c0 = -(dbeta/rows + m2*dgamma/rows)*a
+// which is (du - dbeta/rows - xh*dgamma/rows)*gamma*invstd written so that four constants per channel suffice; keeping
+// them out of registers lets 3-4 blocks share an SM, and that occupancy is what hides the HBM latency of these passes.
+struct ChanConst { float a, b, c, d; };
 
-// du = dz * silu'(u) with u recomputed from y (rounded like the forward), rounded to the activation dtype
-__device__ __forceinline__ float act_bwd(float dz, float u, int act, bool bf16) {
+__device__ __forceinline__ float act_bwd(float dz, float t, int act, bool bf16) {
     if (!act) return dz;
-    const float sg = 1.0f / (1.0f + expf(-u));
-    return round_lowp(dz * sg * (1.0f + u * (1.0f - sg)), bf16);
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-t));
+    return round_lowp(dz * sg * (1.0f + t * (1.0f - sg)), bf16);
 }
 
-__global__ void __launch_bounds__(kRedThreads) bn_act_bwd_reduce_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
-                                                                        int dz_pitch, long long rows, int channels, int bf16, int act,
-                                                                        int cgx, const float* __restrict__ mean,
-                                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                        const float* __restrict__ beta, double* __restrict__ ws) {
+__global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* __restrict__ y, int y_pitch, void* __restrict__ z, int z_pitch,
+                                                                    long long rows, int channels, int bf16, int act, int cgx, int rpb,
+                                                                    float* __restrict__ mean, float* __restrict__ invstd,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    const double* __restrict__ sums, float eps, float momentum,
+                                                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
+    __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
+    for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
+        const int c = blockIdx.x * cgx * 8 + i;
+        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        if (c < channels) {
+            float mu, is;
+            if (sums) {  // batch statistics from the column sums of y5_bn_stats (every block derives what it needs; row-block 0 publishes)
+                const double m = sums[c] / static_cast<double>(rows);
+                double var = sums[channels + c] / static_cast<double>(rows) - m * m;
+                if (var < 0.0) var = 0.0;
+                mu = static_cast<float>(m);
+                is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+                if (blockIdx.y == 0) {
+                    mean[c] = mu;
+                    invstd[c] = is;
+                    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+                    if (running_var) {
+                        const double unbiased = rows > 1 ? var * static_cast<double>(rows) / static_cast<double>(rows - 1) : var;
+                        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+                    }
+                }
+            } else {
+                mu = mean[c];
+                is = invstd[c];
+            }
+            k.a = is * gamma[c];
+            k.b = beta[c] - mu * k.a;
+        }
+        cc[i] = k;
+    }
+    __syncthreads();
+    if (cg * 8 >= channels) return;
+    const bool b = bf16 != 0;
+    const ChanConst* my = cc + tx * 8;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
+    const long long r1 = min(rows, r0 + rpb);
+    for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
+        float v[2][8];
+        const bool two = r + nrows < r1;
+        load8(y, r * y_pitch + cg * 8, b, v[0]);
+        if (two) load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
+                v[u][i] = act ? __fdividef(t, 1.0f + __expf(-t)) : t;
+            }
+            store8(z, (r + u * nrows) * z_pitch + cg * 8, b, v[u]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
+                                                                           int dz_pitch, long long rows, int channels, int bf16, int act,
+                                                                           int cgx, int rpb, const float* __restrict__ mean,
+                                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                           const float* __restrict__ beta, double* __restrict__ ws) {
+    __shared__ ChanConst cc[256];
+    const int nrows = kRedThreads / cgx;
+    const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
+    const int cg = blockIdx.x * cgx + tx;
+    for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
+        const int c = blockIdx.x * cgx * 8 + i;
+        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        if (c < channels) {
+            k.a = invstd[c] * gamma[c];
+            k.b = beta[c] - mean[c] * k.a;
+            k.c = invstd[c];
+            k.d = -mean[c] * invstd[c];
+        }
+        cc[i] = k;
+    }
+    __syncthreads();
     const bool active = cg * 8 < channels;
     const bool b = bf16 != 0;
     float acc[2][8] = {};
     if (active) {
-        float mu[8], is[8], ga[8], be[8];
+        const ChanConst* my = cc + tx * 8;
+        const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
+        const long long r1 = min(rows, r0 + rpb);
+        for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
+            float v[2][8], g[2][8];
+            const bool two = r + nrows < r1;
+            load8(y, r * y_pitch + cg * 8, b, v[0]);
+            load8(dz, r * dz_pitch + cg * 8, b, g[0]);
+            if (two) {
+                load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
+                load8(dz, (r + nrows) * dz_pitch + cg * 8, b, g[1]);
+            }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = cg * 8 + i;
-            mu[i] = mean[c];
-            is[i] = invstd[c];
-            ga[i] = gamma[c];
-            be[i] = beta[c];
-        }
-        const long long r0 = static_cast<long long>(blockIdx.y) * kRowsPerBlock;
-        const long long r1 = min(rows, r0 + kRowsPerBlock);
-        for (long long r = r0 + ty; r < r1; r += nrows) {
-            float v[8], g[8];
-            load8(y, r * y_pitch + cg * 8, b, v);
-            load8(dz, r * dz_pitch + cg * 8, b, g);
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float xh = (v[i] - mu[i]) * is[i];
-                const float u = round_lowp(fmaf(v[i] - mu[i], is[i] * ga[i], be[i]), b);
-                const float du = act_bwd(g[i], u, act, b);
-                acc[0][i] += du;
-                acc[1][i] = fmaf(du, xh, acc[1][i]);
+                for (int i = 0; i < 8; ++i) {
+                    const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
+                    const float du = act_bwd(g[u][i], t, act, b);
+                    acc[0][i] += du;
+                    acc[1][i] = fmaf(du, fmaf(v[u][i], my[i].c, my[i].d), acc[1][i]);
+                }
             }
         }
     }
@@ -203,50 +255,61 @@ __global__ void __launch_bounds__(kRedThreads) bn_act_bwd_reduce_kernel(const vo
     block_publish<2>(acc, cgx, nrows, channels, dst);
 }
 
-__global__ void __launch_bounds__(kRedThreads) bn_act_bwd_apply_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
-                                                                       int dz_pitch, void* __restrict__ dy, int dy_pitch, long long rows,
-                                                                       int channels, int bf16, int act, int cgx,
-                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                       const double* __restrict__ ws, float* __restrict__ dgamma,
-                                                                       float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
+                                                                          int dz_pitch, void* __restrict__ dy, int dy_pitch, long long rows,
+                                                                          int channels, int bf16, int act, int cgx, int rpb,
+                                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                          const double* __restrict__ ws, float* __restrict__ dgamma,
+                                                                          float* __restrict__ dbeta) {
+    __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
+    const float inv_rows = 1.0f / static_cast<float>(rows);
+    for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
+        const int c = blockIdx.x * cgx * 8 + i;
+        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        if (c < channels) {
+            const float db = static_cast<float>(ws[c]), dg = static_cast<float>(ws[channels + c]);
+            if (blockIdx.y == 0) {
+                dbeta[c] = db;
+                dgamma[c] = dg;
+            }
+            const float is = invstd[c], m2 = -mean[c] * is;
+            k.a = is * gamma[c];
+            k.b = beta[c] - mean[c] * k.a;
+            k.c = -is * (dg * inv_rows) * k.a;
+            k.d = -(db * inv_rows + m2 * (dg * inv_rows)) * k.a;
+        }
+        cc[i] = k;
+    }
+    __syncthreads();
     if (cg * 8 >= channels) return;
     const bool b = bf16 != 0;
-    float mu[8], is[8], ga[8], be[8], db[8], dg[8];
-    const float inv_rows = 1.0f / static_cast<float>(rows);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = cg * 8 + i;
-        mu[i] = mean[c];
-        is[i] = invstd[c];
-        ga[i] = gamma[c];
-        be[i] = beta[c];
-        db[i] = static_cast<float>(ws[c]);
-        dg[i] = static_cast<float>(ws[channels + c]);
-        if (blockIdx.y == 0 && ty == 0) {
-            dbeta[c] = db[i];
-            dgamma[c] = dg[i];
+    const ChanConst* my = cc + tx * 8;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
+    const long long r1 = min(rows, r0 + rpb);
+    for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
+        float v[2][8], g[2][8];
+        const bool two = r + nrows < r1;
+        load8(y, r * y_pitch + cg * 8, b, v[0]);
+        load8(dz, r * dz_pitch + cg * 8, b, g[0]);
+        if (two) {
+            load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
+            load8(dz, (r + nrows) * dz_pitch + cg * 8, b, g[1]);
         }
-        db[i] *= inv_rows;
-        dg[i] *= inv_rows;
-    }
-    const long long r0 = static_cast<long long>(blockIdx.y) * kRowsPerBlock;
-    const long long r1 = min(rows, r0 + kRowsPerBlock);
-    for (long long r = r0 + ty; r < r1; r += nrows) {
-        float v[8], g[8];
-        load8(y, r * y_pitch + cg * 8, b, v);
-        load8(dz, r * dz_pitch + cg * 8, b, g);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xh = (v[i] - mu[i]) * is[i];
-            const float u = round_lowp(fmaf(v[i] - mu[i], is[i] * ga[i], be[i]), b);
-            const float du = act_bwd(g[i], u, act, b);
-            v[i] = (du - db[i] - xh * dg[i]) * ga[i] * is[i];
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
+                const float du = act_bwd(g[u][i], t, act, b);
+                v[u][i] = fmaf(du, my[i].a, fmaf(v[u][i], my[i].c, my[i].d));
+            }
+            store8(dy, (r + u * nrows) * dy_pitch + cg * 8, b, v[u]);
         }
-        store8(dy, r * dy_pitch + cg * 8, b, v);
     }
 }
 
@@ -268,6 +331,42 @@ __global__ void zero_stuff2x_kernel(const uint4* __restrict__ in, int in_pitch16
     }
 }
 
+// OIHW master weights (fp32 / fp16 / bf16) -> the two K-major packings the GEMM kernel wants, in one pass:
+//   fwd  [co][r][s][ci_pad]            = w[co][ci][r][s]                  (forward conv)
+//   dgrad[ci][r][s][co_pad]            = w[co][ci][k-1-r][k-1-s]          (data gradient = conv with the flipped, transposed filter)
+__device__ __forceinline__ float load_w(const void* w, long long i, int src_dtype) {
+    if (src_dtype == Y5_F32) return static_cast<const float*>(w)[i];
+    return unpack1(static_cast<const uint16_t*>(w)[i], src_dtype == Y5_BF16);
+}
+__global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, int cout, int cin, int k, uint16_t* __restrict__ fwd, int ci_pad,
+                                   uint16_t* __restrict__ dgrad, int co_pad, int bf16) {
+    const long long n_fwd = fwd ? static_cast<long long>(cout) * k * k * ci_pad : 0;
+    const long long n_dg = dgrad ? static_cast<long long>(cin) * k * k * co_pad : 0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_fwd + n_dg;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        if (i < n_fwd) {
+            const int ci = static_cast<int>(i % ci_pad);
+            long long t = i / ci_pad;
+            const int s_ = static_cast<int>(t % k);
+            t /= k;
+            const int r = static_cast<int>(t % k);
+            const int co = static_cast<int>(t / k);
+            const float v = ci < cin ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + r) * k + s_, src_dtype) : 0.f;
+            fwd[i] = pack1(v, bf16 != 0);
+        } else {
+            const long long j = i - n_fwd;
+            const int co = static_cast<int>(j % co_pad);
+            long long t = j / co_pad;
+            const int s_ = static_cast<int>(t % k);
+            t /= k;
+            const int r = static_cast<int>(t % k);
+            const int ci = static_cast<int>(t / k);
+            const float v = co < cout ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s_), src_dtype) : 0.f;
+            dgrad[j] = pack1(v, bf16 != 0);
+        }
+    }
+}
+
 static int check_view(const void* p, int pitch, int channels, const char* what) {
     if (!p) return set_error(Y5_E_INVALID, "%s: null pointer", what);
     if ((reinterpret_cast<uintptr_t>(p) & 15) || (pitch % 8) || (channels % 8) || channels <= 0 || pitch < channels)
@@ -275,7 +374,7 @@ static int check_view(const void* p, int pitch, int channels, const char* what) 
     return 0;
 }
 static dim3 row_grid(const RowGeom& g, int channels, long long rows) {
-    return dim3((channels / 8 + g.cgx - 1) / g.cgx, static_cast<unsigned>((rows + kRowsPerBlock - 1) / kRowsPerBlock));
+    return dim3((channels / 8 + g.cgx - 1) / g.cgx, static_cast<unsigned>((rows + g.rpb - 1) / g.rpb));
 }
 static int launch_status(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -289,19 +388,14 @@ using namespace y5;
 
 extern "C" Y5_API int64_t y5_bn_workspace_bytes(int32_t channels) { return static_cast<int64_t>(channels) * 2 * sizeof(double); }
 
-extern "C" Y5_API int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, float eps, float momentum,
-                                  float* mean, float* invstd, float* running_mean, float* running_var, void* workspace, void* stream) {
+extern "C" Y5_API int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, int32_t dtype, void* workspace, void* stream) {
     if (int e = check_view(y, pitch, channels, "bn_stats")) return e;
     if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "bn_stats: dtype must be fp16 or bf16");
-    if (!mean || !invstd || !workspace || rows <= 0) return set_error(Y5_E_INVALID, "bn_stats: bad argument");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(workspace, 0, y5_bn_workspace_bytes(channels), st);
-    const RowGeom g = row_geom(channels);
-    count_launch(2);
-    col_stats_kernel<0><<<row_grid(g, channels, rows), kRedThreads, 0, st>>>(y, pitch, rows, channels, dtype == Y5_BF16, g.cgx,
-                                                                              static_cast<double*>(workspace));
-    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<const double*>(workspace), rows, channels, eps, momentum, mean,
-                                                                invstd, running_mean, running_var);
+    if (!workspace || rows <= 0) return set_error(Y5_E_INVALID, "bn_stats: bad argument");
+    const RowGeom g = row_geom(channels, rows, 3);
+    count_launch();
+    col_stats_kernel<0><<<row_grid(g, channels, rows), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb, static_cast<double*>(workspace));
     return launch_status("bn_stats");
 }
 
@@ -312,25 +406,26 @@ extern "C" Y5_API int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int
     if (!out || !workspace || rows <= 0) return set_error(Y5_E_INVALID, "col_sum: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(workspace, 0, static_cast<size_t>(channels) * sizeof(double), st);
-    const RowGeom g = row_geom(channels);
+    const RowGeom g = row_geom(channels, rows, 3);
     count_launch(2);
-    col_stats_kernel<1><<<row_grid(g, channels, rows), kRedThreads, 0, st>>>(y, pitch, rows, channels, dtype == Y5_BF16, g.cgx,
+    col_stats_kernel<1><<<row_grid(g, channels, rows), kRedThreads, 0, st>>>(y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb,
                                                                               static_cast<double*>(workspace));
     col_sum_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<const double*>(workspace), channels, out);
     return launch_status("col_sum");
 }
 
 extern "C" Y5_API int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int64_t rows, int32_t channels, int32_t dtype,
-                                    const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
-                                    void* stream) {
+                                    float* mean, float* invstd, const float* gamma, const float* beta, int32_t act, const void* sums,
+                                    float eps, float momentum, float* running_mean, float* running_var, void* stream) {
     if (int e = check_view(y, y_pitch, channels, "bn_act_fwd y")) return e;
     if (int e = check_view(z, z_pitch, channels, "bn_act_fwd z")) return e;
     if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "bn_act_fwd: dtype must be fp16 or bf16");
     if (!mean || !invstd || !gamma || !beta || rows <= 0) return set_error(Y5_E_INVALID, "bn_act_fwd: bad argument");
-    const RowGeom g = row_geom(channels);
+    const RowGeom g = row_geom(channels, rows, 6);
     count_launch();
     bn_act_fwd_kernel<<<row_grid(g, channels, rows), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, mean, invstd, gamma, beta);
+        y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<const double*>(sums), eps, momentum,
+        running_mean, running_var);
     return launch_status("bn_act_fwd");
 }
 
@@ -344,13 +439,12 @@ extern "C" Y5_API int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* 
     if (!mean || !invstd || !gamma || !beta || !dgamma || !dbeta || !workspace || rows <= 0)
         return set_error(Y5_E_INVALID, "bn_act_bwd: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(workspace, 0, y5_bn_workspace_bytes(channels), st);
-    const RowGeom g = row_geom(channels);
+    const RowGeom g = row_geom(channels, rows, 3), ga = row_geom(channels, rows, 6);
     const dim3 grid = row_grid(g, channels, rows);
     count_launch(2);
-    bn_act_bwd_reduce_kernel<<<grid, kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, mean, invstd,
+    bn_act_bwd_reduce_kernel<<<grid, kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd,
                                                            gamma, beta, static_cast<double*>(workspace));
-    bn_act_bwd_apply_kernel<<<grid, kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx,
+    bn_act_bwd_apply_kernel<<<row_grid(ga, channels, rows), kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, act, ga.cgx, ga.rpb,
                                                           mean, invstd, gamma, beta, static_cast<const double*>(workspace), dgamma, dbeta);
     return launch_status("bn_act_bwd");
 }
@@ -367,4 +461,20 @@ extern "C" Y5_API int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, i
     zero_stuff2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), x_pitch / 8, static_cast<uint4*>(y),
                                                                                y_pitch / 8, batch, h, w, c / 8);
     return launch_status("zero_stuff2x");
+}
+
+extern "C" Y5_API int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t ksize, void* fwd, int32_t in_c_pad,
+                                     void* dgrad, int32_t out_c_pad, int32_t dtype, void* stream) {
+    if (!w || (!fwd && !dgrad)) return set_error(Y5_E_INVALID, "weight_pack: null pointer");
+    if (w_dtype != Y5_F32 && w_dtype != Y5_F16 && w_dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "weight_pack: source dtype");
+    if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "weight_pack: packed dtype must be fp16 or bf16");
+    if (out_c <= 0 || in_c <= 0 || ksize <= 0 || (fwd && in_c_pad < in_c) || (dgrad && out_c_pad < out_c))
+        return set_error(Y5_E_INVALID, "weight_pack: bad shape");
+    const long long total = (fwd ? static_cast<long long>(out_c) * ksize * ksize * in_c_pad : 0) +
+                            (dgrad ? static_cast<long long>(in_c) * ksize * ksize * out_c_pad : 0);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+    count_launch();
+    weight_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_dtype, out_c, in_c, ksize, static_cast<uint16_t*>(fwd), in_c_pad,
+                                                                              static_cast<uint16_t*>(dgrad), out_c_pad, dtype == Y5_BF16);
+    return launch_status("weight_pack");
 }

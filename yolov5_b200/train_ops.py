@@ -25,7 +25,6 @@ import torch.nn.functional as F
 
 from . import _lib
 from ._lib import ConvDesc, WgradDesc
-from .engine import pack_weight, stem_weight_s2d
 
 _CL = torch.channels_last
 
@@ -44,6 +43,17 @@ def _cl(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def _nhwc(x: torch.Tensor):
+    """(tensor, pitch) such that element (n,c,y,x) sits at data_ptr + (((n*H + y)*W + x)*pitch + c) elements: the tensor
+    itself when it is channels_last or a channel slice of a channels_last buffer (what torch.cat's backward hands
+    out), else a dense channels_last copy."""
+    b, c, h, w = x.shape
+    sn, sc, sh, sw = x.stride()
+    if sc == 1 and sw >= c and sw % 8 == 0 and sh == w * sw and sn == h * sh and x.data_ptr() % 16 == 0:
+        return x, sw
+    return _cl(x), c
+
+
 def _empty_cl(b, c, h, w, dtype, device):
     return torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=dtype, device=device)
 
@@ -59,61 +69,104 @@ def _zero_bias(n: int, device) -> torch.Tensor:
     return t
 
 
-def conv_raw(x: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor | None, k: int, s: int, p: int, act: bool = False) -> torch.Tensor:
-    """y = act(conv(x, w) + bias) through y5_conv_bn_silu_fwd.  x: (B,Cin,H,W) channels_last fp16/bf16; w fp32/any OIHW."""
+def _block_k(cin: int, cout: int, m_rows: int) -> int:
+    bk = C.c_int32()
+    _lib.check(_lib.lib().y5_conv_pick(cin, cout, m_rows, C.byref(bk), None), "conv_pick")
+    return bk.value
+
+
+def pack_weights(w: torch.Tensor, dtype: torch.dtype, m_rows: int, want_fwd: bool = True, want_dgrad: bool = False):
+    """OIHW master weights -> (fwd packing [O][k][k][I_pad], dgrad packing [I][k][k][O_pad]) in `dtype`, one launch
+    (y5_weight_pack).  m_rows only steers the K-block choice."""
+    lib = _lib.lib()
+    w = w.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    o, i, k, _ = w.shape
+    fwd = dg = None
+    ipad = opad = bk_f = bk_d = 0
+    if want_fwd:
+        bk_f = _block_k(i, o, m_rows)
+        ipad = (i + bk_f - 1) // bk_f * bk_f
+        fwd = torch.empty(o, k, k, ipad, dtype=dtype, device=w.device)
+    if want_dgrad:
+        bk_d = _block_k(o, i, m_rows)
+        opad = (o + bk_d - 1) // bk_d * bk_d
+        dg = torch.empty(i, k, k, opad, dtype=dtype, device=w.device)
+    _lib.check(lib.y5_weight_pack(w.data_ptr(), _lib.dtype_code(w.dtype), o, i, k, fwd.data_ptr() if fwd is not None else None, ipad,
+                                  dg.data_ptr() if dg is not None else None, opad, _lib.dtype_code(dtype), _st(w.device)), "weight_pack")
+    return fwd, dg, bk_f, bk_d
+
+
+def conv_packed(x: torch.Tensor, x_pitch: int, wp: torch.Tensor, block_k: int, bias32: torch.Tensor | None, cout: int, k: int, s: int, p: int,
+                act: bool = False) -> torch.Tensor:
+    """y = act(conv(x, w) + bias) through y5_conv_bn_silu_fwd.  x: (B,Cin,H,W) NHWC view with row pitch x_pitch; wp: K-major
+    packed weights [cout][k][k][cin_pad]."""
     lib = _lib.lib()
     b, cin, h, w = x.shape
-    cout = w_oihw.shape[0]
     ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     if cin % 8 or cout % 8:
         raise NotImplementedError(f"y5b200: training convs need channel counts that are multiples of 8 (got {cin} -> {cout})")
-    bk, bn = C.c_int32(), C.c_int32()
-    _lib.check(lib.y5_conv_pick(cin, cout, b * ho * wo, C.byref(bk), C.byref(bn)), "conv_pick")
-    wp = pack_weight(w_oihw.detach(), bk.value, x.dtype)
-    bias32 = _zero_bias(cout, x.device) if bias is None else bias.detach().float().contiguous()
+    bias32 = _zero_bias(cout, x.device) if bias32 is None else bias32
     y = _empty_cl(b, cout, ho, wo, x.dtype, x.device)
     d = ConvDesc()
-    d.inp, d.in_pitch = x.data_ptr(), cin
+    d.inp, d.in_pitch = x.data_ptr(), x_pitch
     d.batch, d.in_h, d.in_w, d.in_c = b, h, w, cin
     d.weight, d.bias = wp.data_ptr(), bias32.data_ptr()
     d.out, d.out_pitch, d.out_c = y.data_ptr(), cout, cout
     d.ksize, d.stride, d.pad = k, s, p
     d.act = _lib.ACT_SILU if act else _lib.ACT_NONE
-    d.dtype, d.block_k, d.block_n = _lib.dtype_code(x.dtype), bk.value, 0
+    d.dtype, d.block_k, d.block_n = _lib.dtype_code(x.dtype), block_k, 0
     _lib.check(lib.y5_conv_bn_silu_fwd(C.byref(d), _st(x.device)), "conv fprop/dgrad")
     return y
 
 
-def conv_dgrad(dy: torch.Tensor, w_oihw: torch.Tensor, k: int, s: int, p: int, in_hw: tuple[int, int]) -> torch.Tensor:
+def conv_raw(x: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor | None, k: int, s: int, p: int, act: bool = False) -> torch.Tensor:
+    """One-off conv from OIHW weights (packs them first)."""
+    x, pitch = _nhwc(x)
+    b, cin, h, w = x.shape
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    wp, _, bk, _ = pack_weights(w_oihw, x.dtype, b * ho * wo)
+    bias32 = None if bias is None else bias.detach().float().contiguous()
+    return conv_packed(x, pitch, wp, bk, bias32, w_oihw.shape[0], k, s, p, act)
+
+
+def conv_dgrad(dy: torch.Tensor, w_oihw: torch.Tensor | None, k: int, s: int, p: int, in_hw: tuple[int, int], wp_dgrad: torch.Tensor | None = None,
+               cin: int | None = None, block_k: int = 0) -> torch.Tensor:
     """dx of y = conv(x, w): a stride-1 conv of dy with the flipped, transposed filter (stride-2 layers first expand dy
-    with zeros).  dy: (B,Cout,Ho,Wo) channels_last."""
+    with zeros).  dy: (B,Cout,Ho,Wo) NHWC view; pass either the OIHW weights or their dgrad packing."""
     lib = _lib.lib()
+    dy, pitch = _nhwc(dy)
     b, cout, ho, wo = dy.shape
     if s == 2:
-        if in_hw != (2 * ho, 2 * wo):
+        if tuple(in_hw) != (2 * ho, 2 * wo):
             raise NotImplementedError("y5b200: stride-2 data gradient needs even input height/width")
         z = _empty_cl(b, cout, 2 * ho, 2 * wo, dy.dtype, dy.device)
-        _lib.check(lib.y5_zero_stuff2x(dy.data_ptr(), cout, z.data_ptr(), cout, b, ho, wo, cout, _lib.dtype_code(dy.dtype), _st(dy.device)),
+        _lib.check(lib.y5_zero_stuff2x(dy.data_ptr(), pitch, z.data_ptr(), cout, b, ho, wo, cout, _lib.dtype_code(dy.dtype), _st(dy.device)),
                    "zero_stuff2x")
-        dy = z
+        dy, pitch = z, cout
     elif s != 1:
         raise NotImplementedError(f"y5b200: conv stride {s} backward")
-    wt = w_oihw.detach().flip(2, 3).transpose(0, 1)  # (Cin, Cout, k, k)
-    dx = conv_raw(dy, wt, None, k, 1, k - 1 - p, act=False)
+    if wp_dgrad is None:
+        _, wp_dgrad, _, block_k = pack_weights(w_oihw, dy.dtype, b * in_hw[0] * in_hw[1], want_fwd=False, want_dgrad=True)
+        cin = w_oihw.shape[1]
+    dx = conv_packed(dy, pitch, wp_dgrad, block_k, None, cin, k, 1, k - 1 - p, act=False)
     assert tuple(dx.shape[2:]) == tuple(in_hw), (dx.shape, in_hw)
     return dx
 
 
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, s: int, p: int) -> torch.Tensor:
-    """fp32 dW (Cout,Cin,k,k) of y = conv(x, w) from channels_last x and dy."""
+    """fp32 dW (Cout,Cin,k,k) of y = conv(x, w) from NHWC views of x and dy."""
     lib = _lib.lib()
+    x, xp = _nhwc(x)
+    dy, dp = _nhwc(dy)
     b, cin, h, w = x.shape
     cout = dy.shape[1]
     dw = torch.empty(cout, k, k, cin, dtype=torch.float32, device=x.device)
     d = WgradDesc()
-    d.inp, d.in_pitch = x.data_ptr(), cin
+    d.inp, d.in_pitch = x.data_ptr(), xp
     d.batch, d.in_h, d.in_w, d.in_c = b, h, w, cin
-    d.dout, d.dout_pitch, d.out_c = dy.data_ptr(), cout, cout
+    d.dout, d.dout_pitch, d.out_c = dy.data_ptr(), dp, cout
     d.dweight = dw.data_ptr()
     d.ksize, d.stride, d.pad = k, s, p
     d.dtype, d.accumulate = _lib.dtype_code(x.dtype), 0
@@ -121,8 +174,63 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, s: int, p: int) -> tor
     return dw.permute(0, 3, 1, 2)
 
 
+_stem_idx_cache: dict = {}
+
+
+def _stem_index(device):
+    """gather indices between the (3,6,6) stem filter and its (16,3,3) space-to-depth form (see stem_weight_s2d):
+    fwd[j] = flat (c,ky,kx) source of s2d element j (108 = the appended zero), inv[i] = s2d element holding source i."""
+    key = str(device)
+    if key not in _stem_idx_cache:
+        fwd = torch.full((16 * 9,), 108, dtype=torch.long)
+        inv = torch.zeros(108, dtype=torch.long)
+        for dy in range(2):
+            for dx in range(2):
+                for c in range(3):
+                    for r in range(3):
+                        for q in range(3):
+                            src = (c * 6 + (2 * r + dy)) * 6 + (2 * q + dx)
+                            dst = (((dy * 2 + dx) * 3 + c) * 3 + r) * 3 + q
+                            fwd[dst] = src
+                            inv[src] = dst
+        _stem_idx_cache[key] = (fwd.to(device), inv.to(device))
+    return _stem_idx_cache[key]
+
+
+class _ZeroArena:
+    """fp64 scratch for the per-channel sums of the BN passes.  The kernels want it zero on entry; instead of one memset
+    per layer the whole arena is cleared once at the start of a training forward and handed out in slices (forward and
+    backward of the step both draw from it).  Outside a forward_train (single layers), or when it runs out, slices are
+    freshly zeroed tensors and the arena grows at the next reset."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.want = 1 << 15
+
+    def reset(self, device):
+        if self.buf is None or self.buf.device != device or self.buf.numel() < self.want:
+            self.buf = torch.zeros(self.want, dtype=torch.float64, device=device)
+        else:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, n: int, device) -> torch.Tensor:
+        n = (n + 1) // 2 * 2  # keep 16-byte alignment
+        if self.buf is not None and self.buf.device == device and self.off + n <= self.buf.numel():
+            v = self.buf[self.off : self.off + n]
+            self.off += n
+            return v
+        self.want = max(self.want, 2 * (self.off + n))
+        self.off += n
+        return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+_arena = _ZeroArena()
+
+
 def _bn_ws(c: int, device) -> torch.Tensor:
-    return torch.empty(2 * c, dtype=torch.float64, device=device)
+    return _arena.take(2 * c, device)
 
 
 class _ConvBnAct(torch.autograd.Function):
@@ -133,11 +241,18 @@ class _ConvBnAct(torch.autograd.Function):
         lib = _lib.lib()
         dev = x.device
         if stem:  # x is already the 16-channel space-to-depth image; weight is the (O,3,6,6) stem filter
-            w_eff, ke, se, pe = stem_weight_s2d(weight.detach().float()), 3, 1, 1
+            fwd_idx, _ = _stem_index(dev)
+            wf = weight.detach().flatten(1)
+            w_eff = torch.cat((wf, wf.new_zeros(wf.shape[0], 1)), 1)[:, fwd_idx].view(-1, 16, 3, 3)
+            ke, se, pe = 3, 1, 1
         else:
             w_eff, ke, se, pe = weight, k, s, p
-        x = _cl(x)
-        y = conv_raw(x, w_eff, None, ke, se, pe, act=False)
+        x, xp = _nhwc(x)
+        bsz, _, h, w_ = x.shape
+        m_rows = bsz * ((h + 2 * pe - ke) // se + 1) * ((w_ + 2 * pe - ke) // se + 1)
+        need_dx = ctx.needs_input_grad[0] and not stem
+        wp, wp_dg, bk_f, bk_d = pack_weights(w_eff, x.dtype, m_rows, True, need_dx)
+        y = conv_packed(x, xp, wp, bk_f, None, w_eff.shape[0], ke, se, pe, act=False)
         b, c, ho, wo = y.shape
         rows = b * ho * wo
         code = _lib.dtype_code(y.dtype)
@@ -148,29 +263,32 @@ class _ConvBnAct(torch.autograd.Function):
             # the kernel updates fp32 running statistics in place; a model cast to fp16/bf16 goes through fp32 copies
             rm = running_mean if running_mean is None or running_mean.dtype == torch.float32 else running_mean.float()
             rv = running_var if running_var is None or running_var.dtype == torch.float32 else running_var.float()
-            _lib.check(lib.y5_bn_stats(y.data_ptr(), c, rows, c, code, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
-                                       rm.data_ptr() if rm is not None else None, rv.data_ptr() if rv is not None else None,
-                                       ws.data_ptr(), _st(dev)), "bn_stats")
+            _lib.check(lib.y5_bn_stats(y.data_ptr(), c, rows, c, code, ws.data_ptr(), _st(dev)), "bn_stats")
+            sums = ws.data_ptr()
+        else:
+            mean = running_mean.float().contiguous()
+            invstd = torch.rsqrt(running_var.float() + eps)
+            rm = rv = sums = None
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        z = torch.empty_like(y)
+        _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(),
+                                     b32.data_ptr(), 1 if act else 0, sums, eps, momentum, rm.data_ptr() if rm is not None else None,
+                                     rv.data_ptr() if rv is not None else None, _st(dev)), "bn_act_fwd")
+        if training:
             if rm is not running_mean:
                 running_mean.copy_(rm)
             if rv is not running_var:
                 running_var.copy_(rv)
-        else:
-            mean = running_mean.float()
-            invstd = torch.rsqrt(running_var.float() + eps)
-        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        z = torch.empty_like(y)
-        _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(),
-                                     b32.data_ptr(), 1 if act else 0, _st(dev)), "bn_act_fwd")
-        ctx.save_for_backward(x, weight, y, mean, invstd, g32, b32)
+        ctx.save_for_backward(x, weight, y, mean, invstd, g32, b32, wp_dg)
         ctx.cfg = (k, s, p, act, training, stem, ke, se, pe)
+        ctx.bk_d = bk_d
         ctx.pdtypes = (gamma.dtype, beta.dtype)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         lib = _lib.lib()
-        x, weight, y, mean, invstd, g32, b32 = ctx.saved_tensors
+        x, weight, y, mean, invstd, g32, b32, wp_dg = ctx.saved_tensors
         k, s, p, act, training, stem, ke, se, pe = ctx.cfg
         if not training:
             raise NotImplementedError("y5b200: backward through eval-mode BatchNorm")
@@ -178,27 +296,23 @@ class _ConvBnAct(torch.autograd.Function):
         b, c, ho, wo = y.shape
         rows = b * ho * wo
         code = _lib.dtype_code(y.dtype)
-        dz = _cl(dz.to(y.dtype))
+        dz, dzp = _nhwc(dz if dz.dtype == y.dtype else dz.to(y.dtype))
         dy = torch.empty_like(y)
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         ws = _bn_ws(c, dev)
-        _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), c, dy.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
+        _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), dzp, dy.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
                                      g32.data_ptr(), b32.data_ptr(), 1 if act else 0, dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
                                      _st(dev)), "bn_act_bwd")
         dw = conv_wgrad(x, dy, ke, se, pe)
         if stem:  # (O,16,3,3) gradient of the space-to-depth filter -> (O,3,6,6)
-            full = torch.zeros(weight.shape, dtype=torch.float32, device=dev)
-            for ddy in range(2):
-                for ddx in range(2):
-                    for ch in range(3):
-                        full[:, ch, ddy::2, ddx::2] = dw[:, (ddy * 2 + ddx) * 3 + ch]
-            dw = full
+            _, inv_idx = _stem_index(dev)
+            dw = dw.reshape(dw.shape[0], -1)[:, inv_idx].view(weight.shape)
         dx = None
         if ctx.needs_input_grad[0]:
             if stem:
                 raise NotImplementedError("y5b200: gradient w.r.t. the input image")
-            dx = conv_dgrad(dy, weight, k, s, p, (x.shape[2], x.shape[3]))
+            dx = conv_dgrad(dy, None, k, s, p, (x.shape[2], x.shape[3]), wp_dgrad=wp_dg, cin=x.shape[1], block_k=ctx.bk_d)
         return (dx, dw.to(weight.dtype), dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, None, None, None, None, None, None, None,
                 None)
 
@@ -208,7 +322,7 @@ class _ConvBias(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        x = _cl(x)
+        x, _ = _nhwc(x)
         cout = weight.shape[0]
         cpad = (cout + 7) // 8 * 8
         wpad = torch.zeros(cpad, *weight.shape[1:], dtype=torch.float32, device=x.device)
@@ -347,6 +461,7 @@ def forward_train(model, img: torch.Tensor):
     x = None
     # every op below picks its dtype explicitly; autocast's own casting rules must not touch the glue ops
     with torch.autocast("cuda", enabled=False):
+        _arena.reset(img.device)
         for i, m in enumerate(layers):
             if i == 0:
                 x = conv_module(m, stem_input(img, dt), stem=True)
