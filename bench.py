@@ -41,9 +41,14 @@ WORKLOADS = {  # name -> (model, per-GPU batch, image size, dtype)
     "yolov5n": ("yolov5n", 32, 640, "fp16"),
     "yolov5m": ("yolov5m", 32, 640, "fp16"),
     "yolov5x": ("yolov5x", 16, 640, "fp16"),
+    # training step (BASELINE.json configs[3]: yolov5m, 128 images total = 16 per GPU at 8 GPUs, AMP): forward with
+    # batch-statistics BN + ComputeLoss + backward + SGD step; N > 1 adds DDP's gradient all-reduce (the path's collective)
+    "yolov5m-train": ("yolov5m", 16, 640, "fp16"),
+    "yolov5s-train": ("yolov5s", 16, 640, "fp16"),
 }
 NMS_KW = dict(conf_thres=0.25, iou_thres=0.45, max_det=300)  # detect.py regime (reference detect.py:228 defaults)
 TDT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+_OUT = None
 
 
 def peaks():
@@ -92,6 +97,20 @@ def bench_state_dict(cfg, seed=0, frac=0.02):
             b[a, 4] += float(-0.8473 - q.item())  # the (1-frac) quantile of the objectness logits lands on logit(0.3)
         b[:, 5 : 5 + nc] += 7.0                 # class scores ~0.9
     return sd
+
+
+class StdoutGuard:
+    """Keeps stdout to the single JSON line: while active, fd 1 is pointed at stderr (NCCL prints its version banner to
+    stdout from native code, torchrun children inherit the fd); emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
 
 
 class ClockSampler:
@@ -184,6 +203,194 @@ def cpu_baseline(model_name, size, sample_bs, seed, budget_s=20.0, steps=None, w
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def train_main(a, rank, world, local):
+    """`--workload *-train`: images/s of one optimisation step through the public API (model.train() under autocast,
+    ComputeLoss, backward, clip, SGD), per-GPU batch fixed (weak scaling), gradients all-reduced by DDP for N > 1."""
+    import torch.distributed as dist
+
+    from oracle import loss_ref, model_ref  # synthetic labels / weights, and the torch reference arm
+    from yolov5_b200 import _lib
+    from yolov5_b200.cfg import HYP_SCRATCH_LOW, model_cfg
+    from yolov5_b200.models.yolo import DetectionModel
+    from yolov5_b200.parallel import aggregate_throughput
+    from yolov5_b200.utils.loss import ComputeLoss
+    from yolov5_b200.utils.torch_utils import smart_DDP
+
+    model_name, bs, size, dt = WORKLOADS[a.workload]
+    if a.batch:
+        bs = a.batch
+    tdt = TDT[dt]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    cfg = model_cfg(model_name)
+    sd = model_ref.synth_state_dict(cfg, seed=0)
+    model = DetectionModel(model_name)
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    model.hyp = dict(HYP_SCRATCH_LOW)
+    loss_fn = ComputeLoss(model)
+    net = smart_DDP(model) if world > 1 else model
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.937, nesterov=True, foreach=True)
+    n_rot = 3
+    host_img = [torch.from_numpy(synth_images_u8(bs, size, 2000 + 10 * rank + i)).pin_memory() for i in range(n_rot)]
+    host_tgt = [torch.from_numpy(loss_ref.synth_targets(bs, seed=3000 + 10 * rank + i)).float().pin_memory() for i in range(n_rot)]
+    dev_img = [h.to(dev) for h in host_img]
+    dev_tgt = [h.to(dev) for h in host_tgt]
+
+    def step(img, tgt):
+        with torch.autocast("cuda", dtype=tdt):
+            p = net(img)
+        loss, items = loss_fn(p, tgt)
+        if world > 1:
+            loss = loss * world  # train.py:405: DDP averages gradients, the reference rescales
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)  # train.py:415
+        opt.step()
+        return items
+
+    for i in range(a.warmup):
+        step(dev_img[i % n_rot], dev_tgt[i % n_rot])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for i in range(a.steps):
+        step(dev_img[i % n_rot], dev_tgt[i % n_rot])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - l0
+    images, worst_ms = aggregate_throughput(bs * a.steps, e0.elapsed_time(e1), dev)
+    value = images / (worst_ms / 1e3)
+
+    # e2e: pinned host uint8 images + labels uploaded every step, loss items read back every step
+    host_items = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_run(k):
+        for i in range(k):
+            img = host_img[i % n_rot].to(dev, non_blocking=True)
+            tgt = host_tgt[i % n_rot].to(dev, non_blocking=True)
+            host_items.copy_(step(img, tgt), non_blocking=True)
+
+    e2e_run(2)
+    barrier()
+    e0.record()
+    e2e_run(a.steps)
+    e1.record()
+    barrier()
+    e2e_images, e2e_ms = aggregate_throughput(bs * a.steps, e0.elapsed_time(e1), dev)
+
+    # whole step in one CUDA graph (N = 1): what the kernels cost once Python / launch latency is out of the way
+    graphed = tc_ref = None
+    if rank == 0 and world == 1:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step(dev_img[0], dev_tgt[0])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step(dev_img[0], dev_tgt[0])
+            g.replay()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(a.steps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            graphed = {"value": bs * a.steps / (e0.elapsed_time(e1) / 1e3), "unit": "images/s",
+                       "what": "same step (fixed batch) captured once in a CUDA graph and replayed"}
+            del g
+        except Exception as ex:  # noqa: BLE001
+            graphed = {"unavailable": repr(ex)[:200]}
+    if rank == 0:
+        try:  # the reference's expressions through torch autocast (NCHW, cuDNN), same loss kernel / optimizer / clip
+            params = {k: (torch.nn.Parameter(v.to(dev)) if v.is_floating_point() and "running" not in k and "anchors" not in k
+                          else v.to(dev)) for k, v in sd.items()}
+            plist = [q for q in params.values() if isinstance(q, torch.nn.Parameter)]
+            opt_r = torch.optim.SGD(plist, lr=1e-3, momentum=0.937, nesterov=True, foreach=True)
+
+            def step_ref(img, tgt):
+                x = img.to(tdt) / 255
+                with torch.autocast("cuda", dtype=tdt):
+                    p = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+                loss, _ = loss_fn(p, tgt)
+                opt_r.zero_grad(set_to_none=True)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(plist, max_norm=10.0)
+                opt_r.step()
+
+            for i in range(3):
+                step_ref(dev_img[i % n_rot], dev_tgt[i % n_rot])
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for i in range(a.steps):
+                step_ref(dev_img[i % n_rot], dev_tgt[i % n_rot])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            tc_ref = {"value": bs * a.steps / (e0.elapsed_time(e1) / 1e3), "unit": "images/s",
+                      "what": f"reference expressions under torch.autocast({dt}) on one GPU (no DDP): F.conv2d / batch_norm(training) / "
+                              f"silu / max_pool2d / cat, cuDNN {torch.backends.cudnn.version()}, same loss kernel, clip and SGD"}
+        except Exception as ex:  # noqa: BLE001
+            tc_ref = {"unavailable": repr(ex)[:200]}
+        pk = peaks()
+        # algorithmic bytes of a training step (SURVEY.md 8d convention, layer-fused ideal, 2 B/element): forward reads each
+        # conv input and writes its output once (A); backward reads dy + x for the weight gradient and dy for the data
+        # gradient and writes dx (~2.5 A)
+        prog_bytes = None
+        try:
+            em = DetectionModel(model_name)
+            em.load_state_dict(sd)
+            em = em.to(dev, tdt).eval()
+            prog = em._program(torch.empty(bs, 3, size, size, dtype=tdt, device=dev))
+            prog_bytes = 3.5 * prog.act_bytes + 3 * prog.weight_bytes
+            flops = 3 * prog.flops
+        except Exception:  # noqa: BLE001
+            flops = None
+        ms_step = worst_ms / a.steps
+        roof = None
+        if prog_bytes:
+            gbs = prog_bytes / (ms_step / 1e3) / 1e9
+            roof = {"kernel": "whole training step (conv_gemm fwd+dgrad, conv_wgrad, BN/SiLU passes)", "bound": "hbm", "achieved": gbs,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                    "algorithmic_bytes_per_step": prog_bytes, "flops_per_step": flops,
+                    "tensor_tflops": flops / (ms_step / 1e3) / 1e12 if flops else None}
+        line = {"metric": "images/sec @640 (training step: forward + loss + backward + SGD)", "value": value, "unit": "images/s",
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16" if dt == "fp16" else "bf16", "data": "synthetic",
+                "config": {"workload": f"{model_name} training step, bs={bs}/GPU, {size}x{size}, autocast {dt}, fp32 master weights",
+                           "model": model_name, "per_gpu_batch": bs, "global_batch": bs * world,
+                           "parallelism": f"dp{world} (DDP gradient all-reduce over NCCL)" if world > 1 else "single GPU",
+                           "l2": "3 rotating batches; a step streams GBs of activations",
+                           "labels": "COCO128-shaped synthetic targets (oracle.loss_ref.synth_targets), ~7.3 per image"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": bs * 3 * size * size + int(host_tgt[0].numel()) * 4,
+                        "d2h_bytes_per_step": 12},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": None, "cuda_graph_step": graphed,
+                "torch_cuda_reference_train": tc_ref}
+        _OUT.emit(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,10 +402,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    global _OUT
+    _OUT = StdoutGuard()
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.workload.endswith("-train"):
+        if a.impl == "reference":
+            if rank == 0:
+                _OUT.emit(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm covers the inference metric only; the "
+                                      "training workload reports torch_cuda_reference_train instead"}))
+            return 0
+        return train_main(a, rank, world, local)
     model_name, bs, size, dt = WORKLOADS[a.workload]
     if a.batch:
         bs = a.batch
@@ -218,7 +434,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        _OUT.emit(json.dumps(line))
         return 0
 
     import torch.distributed as dist
@@ -414,7 +630,7 @@ def main():
                 "e2e": {"value": e2e_images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(eager_launches + graph_launches), "roofline": roof, "cpu_baseline": cb,
                 "forward_only": {"value": fwd_only, "unit": "images/s"}, "torch_cuda_reference_forward": tc_ref}
-        print(json.dumps(line), flush=True)
+        _OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

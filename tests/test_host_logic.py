@@ -95,3 +95,74 @@ def test_module_pickles_without_engine_state():
     m2 = pickle.loads(pickle.dumps(m))
     assert "_y5_programs" not in m2.__dict__
     assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host logic of the training path (no GPU): index maps, NHWC view detection, zero arena
+# ---------------------------------------------------------------------------------------------------------------------
+def test_stem_index_maps_match_stem_weight_s2d():
+    """train_ops._stem_index must be the gather form of engine.stem_weight_s2d and its exact inverse on the 108 taps."""
+    import torch
+
+    from yolov5_b200 import train_ops
+    from yolov5_b200.engine import stem_weight_s2d
+
+    w = torch.arange(32 * 3 * 6 * 6, dtype=torch.float32).view(32, 3, 6, 6) + 1
+    fwd, inv = train_ops._stem_index(torch.device("cpu"))
+    wf = w.flatten(1)
+    gathered = torch.cat((wf, wf.new_zeros(32, 1)), 1)[:, fwd].view(32, 16, 3, 3)
+    assert torch.equal(gathered, stem_weight_s2d(w))
+    assert torch.equal(gathered.reshape(32, -1)[:, inv].view(32, 3, 6, 6), w)  # the weight-gradient path back to (O,3,6,6)
+    assert int((fwd == 108).sum()) == 36  # 4 unused channels x 9 taps read the appended zero
+
+
+def test_nhwc_view_detection():
+    import torch
+
+    from yolov5_b200 import train_ops
+
+    buf = torch.zeros(2, 5, 7, 48, dtype=torch.float16)  # NHWC memory
+    x = buf.permute(0, 3, 1, 2)                            # logical NCHW, channels_last
+    t, pitch = train_ops._nhwc(x)
+    assert t.data_ptr() == x.data_ptr() and pitch == 48
+    sl = x[:, 16:32]                                       # channel slice (what torch.cat's backward produces)
+    t, pitch = train_ops._nhwc(sl)
+    assert t.data_ptr() == sl.data_ptr() and pitch == 48 and t.shape[1] == 16
+    odd = x[:, 4:20]                                       # 8-byte aligned only: must be copied to a dense tensor
+    t, pitch = train_ops._nhwc(odd)
+    assert t.data_ptr() != odd.data_ptr() and pitch == 16 and torch.equal(t, odd)
+    nchw = torch.zeros(2, 16, 5, 7, dtype=torch.float16)   # NCHW-contiguous input gets a channels_last copy
+    t, pitch = train_ops._nhwc(nchw)
+    assert pitch == 16 and t.stride() == (5 * 7 * 16, 1, 7 * 16, 16)
+
+
+def test_zero_arena_slices_are_disjoint_and_zero():
+    import torch
+
+    from yolov5_b200.train_ops import _ZeroArena
+
+    a = _ZeroArena()
+    dev = torch.device("cpu")
+    first = a.take(10, dev)  # before any reset: a fresh zero tensor
+    assert first.numel() == 10 and float(first.abs().sum()) == 0
+    a.reset(dev)
+    s1, s2 = a.take(6, dev), a.take(7, dev)
+    assert s1.data_ptr() + 6 * 8 <= s2.data_ptr() and s2.numel() == 8  # rounded to 16 bytes
+    s1.fill_(3.0)
+    a.reset(dev)
+    assert float(a.take(6, dev).abs().sum()) == 0  # cleared by the reset
+    big = a.take(1 << 20, dev)  # beyond capacity: fallback allocation, and the arena grows at the next reset
+    assert big.numel() == 1 << 20 and float(big.abs().sum()) == 0
+    a.reset(dev)
+    assert a.buf.numel() >= 1 << 20
+
+
+def test_training_forward_rejects_cpu_and_fp32():
+    import pytest
+    import torch
+
+    from yolov5_b200.models.yolo import DetectionModel
+
+    m = DetectionModel("yolov5n").train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 64, 64))

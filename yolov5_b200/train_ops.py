@@ -171,7 +171,9 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, s: int, p: int) -> tor
     d.ksize, d.stride, d.pad = k, s, p
     d.dtype, d.accumulate = _lib.dtype_code(x.dtype), 0
     _lib.check(lib.y5_conv_wgrad(C.byref(d), _st(x.device)), "conv_wgrad")
-    return dw.permute(0, 3, 1, 2)
+    if k == 1:
+        return dw.view(cout, cin, 1, 1)  # KRSC == OIHW for 1x1 filters
+    return dw.permute(0, 3, 1, 2).contiguous()  # gradients must be laid out like the parameter (DDP buckets, optimizers)
 
 
 _stem_idx_cache: dict = {}
