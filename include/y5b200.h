@@ -239,10 +239,12 @@ int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, int32_t channels, in
 /* z = act(gamma * (y - mean) * invstd + beta), act: Y5_ACT_NONE | Y5_ACT_SILU; z may be a channel-slice view.
  * sums != NULL (training): mean / invstd (biased variance + eps) are first derived from the y5_bn_stats workspace and
  * WRITTEN to mean / invstd, and running_mean / running_var (nullable) are updated like nn.BatchNorm2d does (momentum,
- * unbiased variance).  sums == NULL (eval): mean / invstd are inputs. */
+ * unbiased variance).  sums == NULL (eval): mean / invstd are inputs.  residual != NULL adds a view of the same shape
+ * after the activation (Bottleneck shortcut, models/common.py:181); its gradient is dz itself. */
 int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int64_t rows, int32_t channels,
                   int32_t dtype, float* mean, float* invstd, const float* gamma, const float* beta, int32_t act,
-                  const void* sums, float eps, float momentum, float* running_mean, float* running_var, void* stream);
+                  const void* sums, float eps, float momentum, float* running_mean, float* running_var,
+                  const void* residual, int32_t res_pitch, void* stream);
 /* given dz: dy (gradient w.r.t. the conv output), dgamma, dbeta (fp32, overwritten) */
 int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* dz, int32_t dz_pitch, void* dy, int32_t dy_pitch,
                   int64_t rows, int32_t channels, int32_t dtype, const float* mean, const float* invstd,
@@ -256,6 +258,16 @@ int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int32_t channels, int
  * (padding channels zero; pads = channel counts rounded up to the block_k y5_conv_pick returns). */
 int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t ksize, void* fwd, int32_t in_c_pad,
                    void* dgrad, int32_t out_c_pad, int32_t dtype, void* stream);
+/* backward of y5_upsample2x: dx[n,i,j,:] = dy[n,2i,2j,:] + dy[n,2i,2j+1,:] + dy[n,2i+1,2j,:] + dy[n,2i+1,2j+1,:] */
+int y5_upsample2x_bwd(const void* dy, int32_t dy_pitch, void* dx, int32_t dx_pitch, int32_t batch, int32_t h, int32_t w,
+                      int32_t c, int32_t dtype, void* stream);
+/* backward of y5_sppf_pool + the concat of SPPF (models/common.py:338-340): cat = [a, m(a), m(m(a)), m(m(m(a)))] as 4
+ * channel slices of c channels (the forward's buffer), dcat its gradient; writes da.  Arg-max ties resolve to the
+ * first maximum in row-major window order, as torch's max_pool2d backward does.  workspace: 3*B*h*w*c floats. */
+int64_t y5_sppf_bwd_workspace_bytes(int32_t batch, int32_t h, int32_t w, int32_t c);
+int y5_sppf_pool_bwd(const void* cat, int32_t cat_pitch, const void* dcat, int32_t dcat_pitch, void* da, int32_t da_pitch,
+                     int32_t batch, int32_t h, int32_t w, int32_t c, int32_t ksize, int32_t dtype, void* workspace,
+                     void* stream);
 /* y[n, 2i, 2j, :] = x[n, i, j, :], other pixels of the (2h, 2w) output zero */
 int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int32_t batch, int32_t h, int32_t w,
                     int32_t c, int32_t dtype, void* stream);

@@ -81,7 +81,7 @@ def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
     z = torch.empty_like(y)
     _lib.check(lib.y5_bn_stats(y.data_ptr(), C_, rows, C_, code, ws.data_ptr(), st))
     _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                 beta.data_ptr(), 1, ws.data_ptr(), 1e-3, 0.03, rm.data_ptr(), rv.data_ptr(), st))
+                                 beta.data_ptr(), 1, ws.data_ptr(), 1e-3, 0.03, rm.data_ptr(), rv.data_ptr(), None, 0, st))
     yd = y.double().permute(0, 2, 3, 1).reshape(rows, C_)
     m_ref, v_ref = yd.mean(0), yd.var(0, unbiased=False)
     assert torch.allclose(mean.double(), m_ref, rtol=1e-5, atol=1e-6)
@@ -92,7 +92,7 @@ def test_bn_silu_train_kernels(cuda, C_, rows_hw, dtype):
     # eval form (statistics given) must produce the same output
     z2 = torch.empty_like(y)
     _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), C_, z2.data_ptr(), C_, rows, C_, code, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                 beta.data_ptr(), 1, None, 1e-3, 0.03, None, None, st))
+                                 beta.data_ptr(), 1, None, 1e-3, 0.03, None, None, None, 0, st))
     assert torch.equal(z, z2)
     u = ((y.float() - mean.view(1, -1, 1, 1)) * (invstd * gamma).view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)).to(dtype)
     z_ref = F.silu(u.float()).to(dtype)
@@ -127,6 +127,69 @@ def test_col_sum_and_zero_stuff(cuda):
     ref = torch.zeros_like(z)
     ref[:, :, ::2, ::2] = x
     assert torch.equal(z, ref)
+
+
+def test_upsample_and_concat_functions(cuda):
+    x = _cl_rand((2, 32, 6, 10), torch.float16, cuda, 11).requires_grad_(True)
+    y = train_ops._Upsample2x.apply(x)
+    ref = F.interpolate(x.detach().float(), scale_factor=2.0, mode="nearest")
+    assert torch.equal(y.float(), ref)
+    g = _cl_rand(tuple(y.shape), torch.float16, cuda, 12)
+    y.backward(g)
+    gr = F.avg_pool2d(g.float(), 2) * 4
+    assert float((x.grad.float() - gr).abs().max()) <= 2e-3 * float(gr.abs().max())
+    a = _cl_rand((2, 16, 5, 7), torch.float16, cuda, 13).requires_grad_(True)
+    b = _cl_rand((2, 40, 5, 7), torch.float16, cuda, 14).requires_grad_(True)
+    c = train_ops._Concat.apply(a, b)
+    assert torch.equal(c, torch.cat((a.detach(), b.detach()), 1))
+    gc = _cl_rand(tuple(c.shape), torch.float16, cuda, 15)
+    c.backward(gc)
+    assert torch.equal(a.grad, gc[:, :16]) and torch.equal(b.grad, gc[:, 16:])
+
+
+@pytest.mark.parametrize("levels", [4, 1000])  # 4 distinct values: arg-max ties everywhere (torch keeps the first maximum)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_sppf_pool_cat_forward_backward(cuda, levels, dtype):
+    gen = torch.Generator().manual_seed(16)
+    a0 = (torch.randint(0, levels, (2, 32, 11, 13), generator=gen).float() / levels - 0.5).to(dtype)
+    a = a0.to(cuda).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    cat = train_ops._SppfPoolCat.apply(a, 5)
+    ar = a0.to(cuda).float().requires_grad_(True)
+    y1 = F.max_pool2d(ar, 5, 1, 2)
+    y2 = F.max_pool2d(y1, 5, 1, 2)
+    y3 = F.max_pool2d(y2, 5, 1, 2)
+    ref = torch.cat((ar, y1, y2, y3), 1)
+    assert torch.equal(cat.float(), ref.detach())
+    g = _cl_rand(tuple(cat.shape), dtype, cuda, 17)
+    cat.backward(g)
+    ref.backward(g.float())
+    tol = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert float((a.grad.float() - ar.grad).abs().max()) <= tol * float(ar.grad.abs().max())
+
+
+def test_bottleneck_residual_in_bn_pass(cuda):
+    """Bottleneck(c, c).train(): the shortcut is an operand of cv2's normalise+activate kernel; both gradient paths of x."""
+    from yolov5_b200.models.common import Bottleneck
+
+    torch.manual_seed(1)
+    m = Bottleneck(32, 32, shortcut=True, e=1.0).to(cuda).train()
+    for bn in (m.cv1.bn, m.cv2.bn):
+        bn.eps, bn.momentum = 1e-3, 0.03
+    x = _cl_rand((2, 32, 12, 12), torch.float16, cuda, 18).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        z = m(x)
+    dz = _cl_rand(tuple(z.shape), torch.float16, cuda, 19)
+    z.backward(dz)
+
+    def conv(mm, t, k):
+        w = mm.conv.weight.detach().half().float()
+        return F.silu(F.batch_norm(F.conv2d(t, w, None, 1, k // 2), None, None, mm.bn.weight.detach(), mm.bn.bias.detach(), training=True, eps=1e-3))
+
+    xr = x.detach().float().requires_grad_(True)
+    zr = xr + conv(m.cv2, conv(m.cv1, xr, 1), 3)
+    zr.backward(dz.float())
+    assert float((z.detach().float() - zr.detach()).abs().max()) <= 8e-3 * float(zr.abs().max())
+    assert float((x.grad.float() - xr.grad).abs().max()) <= 2e-2 * float(xr.grad.abs().max())
 
 
 @pytest.mark.parametrize("k,s", [(1, 1), (3, 1), (3, 2)])

@@ -53,7 +53,7 @@ def main():
 
         t_stats = graph_time(lambda: lib.y5_bn_stats(y.data_ptr(), c, rows, c, code, ws.data_ptr(), st()))
         t_fwd = graph_time(lambda: lib.y5_bn_act_fwd(y.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
-                                                     gamma.data_ptr(), beta.data_ptr(), 1, None, 1e-3, 0.03, None, None, st()))
+                                                     gamma.data_ptr(), beta.data_ptr(), 1, None, 1e-3, 0.03, None, None, None, 0, st()))
         t_bwd = graph_time(lambda: lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(),
                                                      invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, dg.data_ptr(), db.data_ptr(),
                                                      ws.data_ptr(), st()))

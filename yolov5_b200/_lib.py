@@ -116,7 +116,10 @@ SIGNATURES = {
     "y5_conv_wgrad": (_I32, [C.POINTER(WgradDesc), _P]),
     "y5_bn_workspace_bytes": (_I64, [_I32]),
     "y5_bn_stats": (_I32, [_P, _I32, _I64, _I32, _I32, _P, _P]),
-    "y5_bn_act_fwd": (_I32, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _F, _F, _P, _P, _P]),
+    "y5_bn_act_fwd": (_I32, [_P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _F, _F, _P, _P, _P, _I32, _P]),
+    "y5_upsample2x_bwd": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "y5_sppf_bwd_workspace_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "y5_sppf_pool_bwd": (_I32, [_P, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "y5_bn_act_bwd": (_I32, [_P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "y5_col_sum": (_I32, [_P, _I32, _I64, _I32, _I32, _P, _P, _P]),
     "y5_weight_pack": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _I32, _P]),

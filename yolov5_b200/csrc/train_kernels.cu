@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* 
                                                                     float* __restrict__ mean, float* __restrict__ invstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     const double* __restrict__ sums, float eps, float momentum,
-                                                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
+                                                                    float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                    const void* __restrict__ res, int res_pitch) {
     __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
@@ -184,10 +185,14 @@ __global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* 
     const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
     const long long r1 = min(rows, r0 + rpb);
     for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
-        float v[2][8];
+        float v[2][8], q[2][8];
         const bool two = r + nrows < r1;
         load8(y, r * y_pitch + cg * 8, b, v[0]);
         if (two) load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
+        if (res) {  // Bottleneck shortcut (models/common.py:181): z = x + SiLU(BN(y)), each term rounded like the reference's add
+            load8(res, r * res_pitch + cg * 8, b, q[0]);
+            if (two) load8(res, (r + nrows) * res_pitch + cg * 8, b, q[1]);
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !two) break;
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* 
             for (int i = 0; i < 8; ++i) {
                 const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
                 v[u][i] = act ? __fdividef(t, 1.0f + __expf(-t)) : t;
+                if (res) v[u][i] = round_lowp(v[u][i], b) + q[u][i];
             }
             store8(z, (r + u * nrows) * z_pitch + cg * 8, b, v[u]);
         }
@@ -367,6 +373,84 @@ __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, in
     }
 }
 
+// backward of nn.Upsample(scale_factor=2, 'nearest'): dx[n,y,x,:] = sum of the 2x2 block of dy (fp32 sum, one rounding)
+__global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, int dy_pitch, void* __restrict__ dx, int dx_pitch, int B, int H, int W, int C,
+                                      int bf16) {
+    const int cv = C >> 3;
+    const long long total = static_cast<long long>(B) * H * W * cv;
+    const bool b = bf16 != 0;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % cv);
+        const long long pix = idx / cv;
+        const int x = static_cast<int>(pix % W);
+        const int y = static_cast<int>((pix / W) % H);
+        const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        float acc[8] = {};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[8];
+            load8(dy, ((static_cast<long long>(n) * 2 * H + 2 * y + (j >> 1)) * 2 * W + 2 * x + (j & 1)) * dy_pitch + c8 * 8, b, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+        store8(dx, pix * dx_pitch + c8 * 8, b, acc);
+    }
+}
+
+// ---- backward of SPPF's pooling chain  cat = [a, y1 = m(a), y2 = m(y1), y3 = m(y2)], m = MaxPool2d(k, 1, k/2) ----
+// acc_j (fp32, dense [B*H*W][c]) start as the incoming gradients of slices 0..2; then, last stage first, every output
+// position routes its gradient to the arg-max of its window (first maximum in row-major scan order, strict '>', as
+// torch's max_pool2d_with_indices picks it):  g3 -> acc2 through y2's windows, acc2 -> acc1 through y1's, acc1 -> acc0
+// through a's.  acc0 rounded is da.
+__global__ void sppf_bwd_init_kernel(const void* __restrict__ dcat, int dcat_pitch, float* __restrict__ acc, long long pixels, int c, int bf16) {
+    const long long total = pixels * c;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(i / total);
+        const long long e = i - j * total;
+        const long long pix = e / c;
+        const int ch = static_cast<int>(e - pix * c);
+        acc[i] = unpack1(static_cast<const uint16_t*>(dcat)[pix * dcat_pitch + j * c + ch], bf16 != 0);
+    }
+}
+template <bool G_LOWP>
+__global__ void sppf_bwd_scatter_kernel(const void* __restrict__ src, int src_pitch, const void* __restrict__ g, int g_pitch,
+                                        float* __restrict__ acc, int B, int H, int W, int c, int k, int bf16) {
+    const long long total = static_cast<long long>(B) * H * W * c;
+    const int r = k / 2;
+    const bool b = bf16 != 0;
+    const uint16_t* s = static_cast<const uint16_t*>(src);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % c);
+        const long long pix = i / c;
+        const int x = static_cast<int>(pix % W);
+        const int y = static_cast<int>((pix / W) % H);
+        const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        const float gv = G_LOWP ? unpack1(static_cast<const uint16_t*>(g)[pix * g_pitch + ch], b) : static_cast<const float*>(g)[pix * g_pitch + ch];
+        float best = -INFINITY;
+        long long arg = -1;
+        for (int yy = max(0, y - r); yy <= min(H - 1, y + r); ++yy)
+            for (int xx = max(0, x - r); xx <= min(W - 1, x + r); ++xx) {
+                const long long q = (static_cast<long long>(n) * H + yy) * W + xx;
+                const float v = unpack1(s[q * src_pitch + ch], b);
+                if (v > best || arg < 0 || v != v) {
+                    best = v;
+                    arg = q;
+                }
+            }
+        if (gv != 0.f) atomicAdd(acc + arg * c + ch, gv);
+    }
+}
+__global__ void f32_to_lowp_kernel(const float* __restrict__ in, void* __restrict__ out, int out_pitch, long long pixels, int c, int bf16) {
+    const long long total = pixels * c;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / c;
+        static_cast<uint16_t*>(out)[pix * out_pitch + (i - pix * c)] = pack1(in[i], bf16 != 0);
+    }
+}
+
 static int check_view(const void* p, int pitch, int channels, const char* what) {
     if (!p) return set_error(Y5_E_INVALID, "%s: null pointer", what);
     if ((reinterpret_cast<uintptr_t>(p) & 15) || (pitch % 8) || (channels % 8) || channels <= 0 || pitch < channels)
@@ -416,16 +500,19 @@ extern "C" Y5_API int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int
 
 extern "C" Y5_API int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int64_t rows, int32_t channels, int32_t dtype,
                                     float* mean, float* invstd, const float* gamma, const float* beta, int32_t act, const void* sums,
-                                    float eps, float momentum, float* running_mean, float* running_var, void* stream) {
+                                    float eps, float momentum, float* running_mean, float* running_var, const void* residual,
+                                    int32_t res_pitch, void* stream) {
     if (int e = check_view(y, y_pitch, channels, "bn_act_fwd y")) return e;
     if (int e = check_view(z, z_pitch, channels, "bn_act_fwd z")) return e;
     if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "bn_act_fwd: dtype must be fp16 or bf16");
     if (!mean || !invstd || !gamma || !beta || rows <= 0) return set_error(Y5_E_INVALID, "bn_act_fwd: bad argument");
+    if (residual)
+        if (int e = check_view(residual, res_pitch, channels, "bn_act_fwd residual")) return e;
     const RowGeom g = row_geom(channels, rows, 6);
     count_launch();
     bn_act_fwd_kernel<<<row_grid(g, channels, rows), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<const double*>(sums), eps, momentum,
-        running_mean, running_var);
+        running_mean, running_var, residual, res_pitch);
     return launch_status("bn_act_fwd");
 }
 
@@ -477,4 +564,47 @@ extern "C" Y5_API int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out
     weight_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_dtype, out_c, in_c, ksize, static_cast<uint16_t*>(fwd), in_c_pad,
                                                                               static_cast<uint16_t*>(dgrad), out_c_pad, dtype == Y5_BF16);
     return launch_status("weight_pack");
+}
+
+extern "C" Y5_API int y5_upsample2x_bwd(const void* dy, int32_t dy_pitch, void* dx, int32_t dx_pitch, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                        int32_t dtype, void* stream) {
+    if (int e = check_view(dy, dy_pitch, c, "upsample2x_bwd dy")) return e;
+    if (int e = check_view(dx, dx_pitch, c, "upsample2x_bwd dx")) return e;
+    if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "upsample2x_bwd: dtype must be fp16 or bf16");
+    if (batch <= 0 || h <= 0 || w <= 0) return set_error(Y5_E_INVALID, "upsample2x_bwd: bad shape");
+    const long long total = static_cast<long long>(batch) * h * w * (c / 8);
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+    count_launch();
+    upsample2x_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dy_pitch, dx, dx_pitch, batch, h, w, c, dtype == Y5_BF16);
+    return launch_status("upsample2x_bwd");
+}
+
+extern "C" Y5_API int64_t y5_sppf_bwd_workspace_bytes(int32_t batch, int32_t h, int32_t w, int32_t c) {
+    return static_cast<int64_t>(3) * batch * h * w * c * sizeof(float);
+}
+
+extern "C" Y5_API int y5_sppf_pool_bwd(const void* cat, int32_t cat_pitch, const void* dcat, int32_t dcat_pitch, void* da, int32_t da_pitch,
+                                       int32_t batch, int32_t h, int32_t w, int32_t c, int32_t ksize, int32_t dtype, void* workspace,
+                                       void* stream) {
+    if (int e = check_view(cat, cat_pitch, c, "sppf_pool_bwd cat")) return e;
+    if (int e = check_view(dcat, dcat_pitch, c, "sppf_pool_bwd dcat")) return e;
+    if (int e = check_view(da, da_pitch, c, "sppf_pool_bwd da")) return e;
+    if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "sppf_pool_bwd: dtype must be fp16 or bf16");
+    if (!workspace || batch <= 0 || h <= 0 || w <= 0 || ksize < 1 || !(ksize & 1) || cat_pitch < 4 * c || dcat_pitch < 4 * c)
+        return set_error(Y5_E_INVALID, "sppf_pool_bwd: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long pixels = static_cast<long long>(batch) * h * w, total = pixels * c;
+    const int bf = dtype == Y5_BF16;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+    float* acc = static_cast<float*>(workspace);
+    const uint16_t* cat16 = static_cast<const uint16_t*>(cat);
+    const uint16_t* dcat16 = static_cast<const uint16_t*>(dcat);
+    count_launch(5);
+    sppf_bwd_init_kernel<<<blocks, 256, 0, st>>>(dcat, dcat_pitch, acc, pixels, c, bf);
+    // g3 -> acc2 through the windows of y2 (slice 2);  acc2 -> acc1 through y1 (slice 1);  acc1 -> acc0 through a (slice 0)
+    sppf_bwd_scatter_kernel<true><<<blocks, 256, 0, st>>>(cat16 + 2 * c, cat_pitch, dcat16 + 3 * c, dcat_pitch, acc + 2 * total, batch, h, w, c, ksize, bf);
+    sppf_bwd_scatter_kernel<false><<<blocks, 256, 0, st>>>(cat16 + c, cat_pitch, acc + 2 * total, c, acc + total, batch, h, w, c, ksize, bf);
+    sppf_bwd_scatter_kernel<false><<<blocks, 256, 0, st>>>(cat16, cat_pitch, acc + total, c, acc, batch, h, w, c, ksize, bf);
+    f32_to_lowp_kernel<<<blocks, 256, 0, st>>>(acc, da, da_pitch, pixels, c, bf);
+    return launch_status("sppf_pool_bwd");
 }

@@ -9,9 +9,11 @@ What runs where
     SiLU forward / backward: liby5b200 kernels (tcgen05 implicit GEMMs + HBM-bound passes), wrapped in
     torch.autograd.Function so gradients land in the ordinary ``.grad`` of the nn.Parameters (DDP's bucketed NCCL
     all-reduce -- smart_DDP -- works unchanged);
-  * the data-movement glue between convolutions (channel concat, 2x nearest upsample, 5x5 max-pool, residual add) is
-    left to torch autograd in this first training path.  Activations are channels_last, so those ops read and write
-    the same NHWC bytes the kernels use and no layout conversion happens anywhere.
+  * the glue between convolutions is liby5b200 too: channel concat = strided slice copies whose backward is a set of
+    views, 2x nearest upsample and its 2x2-sum backward, SPPF's pooling chain and its arg-max backward, the Bottleneck
+    shortcut as a residual operand of cv2's normalise+activate pass.  What is left to torch autograd is bookkeeping: the
+    graph itself, summing gradients of tensors with several consumers, the (B,na,ny,nx,no) permute of the head output.
+    Activations are channels_last, so every op reads and writes the same NHWC bytes and no layout conversion exists.
 
 Precision: activations and their gradients in fp16/bf16 (the autocast dtype, or the parameter dtype if the model was
 cast), BN statistics / affine gradients / weight gradients in fp32 -- the reference's AMP recipe.
@@ -21,7 +23,6 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from ._lib import ConvDesc, WgradDesc
@@ -239,7 +240,7 @@ class _ConvBnAct(torch.autograd.Function):
     """z = act(BN(conv(x, w)))  with batch statistics (training) or running statistics (eval inside a training graph)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, k, s, p, act, eps, momentum, training, stem):
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, k, s, p, act, eps, momentum, training, stem):
         lib = _lib.lib()
         dev = x.device
         if stem:  # x is already the 16-channel space-to-depth image; weight is the (O,3,6,6) stem filter
@@ -273,9 +274,11 @@ class _ConvBnAct(torch.autograd.Function):
             rm = rv = sums = None
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         z = torch.empty_like(y)
+        res, resp = (None, 0) if residual is None else _nhwc(residual)
         _lib.check(lib.y5_bn_act_fwd(y.data_ptr(), c, z.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(),
                                      b32.data_ptr(), 1 if act else 0, sums, eps, momentum, rm.data_ptr() if rm is not None else None,
-                                     rv.data_ptr() if rv is not None else None, _st(dev)), "bn_act_fwd")
+                                     rv.data_ptr() if rv is not None else None, res.data_ptr() if res is not None else None, resp,
+                                     _st(dev)), "bn_act_fwd")
         if training:
             if rm is not running_mean:
                 running_mean.copy_(rm)
@@ -298,6 +301,7 @@ class _ConvBnAct(torch.autograd.Function):
         b, c, ho, wo = y.shape
         rows = b * ho * wo
         code = _lib.dtype_code(y.dtype)
+        dz_in = dz
         dz, dzp = _nhwc(dz if dz.dtype == y.dtype else dz.to(y.dtype))
         dy = torch.empty_like(y)
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
@@ -315,8 +319,9 @@ class _ConvBnAct(torch.autograd.Function):
             if stem:
                 raise NotImplementedError("y5b200: gradient w.r.t. the input image")
             dx = conv_dgrad(dy, None, k, s, p, (x.shape[2], x.shape[3]), wp_dgrad=wp_dg, cin=x.shape[1], block_k=ctx.bk_d)
-        return (dx, dw.to(weight.dtype), dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, None, None, None, None, None, None, None,
-                None)
+        dres = dz_in if ctx.needs_input_grad[6] else None  # z = residual + act(bn(y)): the shortcut's gradient is dz itself
+        return (dx, dw.to(weight.dtype), dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, dres, None, None, None, None, None,
+                None, None, None)
 
 
 class _ConvBias(torch.autograd.Function):
@@ -370,7 +375,7 @@ def train_dtype(model) -> torch.dtype:
     return dt
 
 
-def conv_module(m, x, stem: bool = False):
+def conv_module(m, x, stem: bool = False, residual=None):
     bn = getattr(m, "bn", None)
     if bn is None:
         raise RuntimeError("y5b200: cannot train a fused model (Conv without BatchNorm); build it unfused")
@@ -386,8 +391,92 @@ def conv_module(m, x, stem: bool = False):
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     mom = bn.momentum if bn.momentum is not None else 0.1
-    return _ConvBnAct.apply(x, m.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, k, s, p, act, float(bn.eps), float(mom),
-                            training, stem)
+    return _ConvBnAct.apply(x, m.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, k, s, p, act, float(bn.eps),
+                            float(mom), training, stem)
+
+
+class _Upsample2x(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='nearest') (models/yolov5s.yaml:36,41) and its backward (sum of each 2x2 block)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x, xp = _nhwc(x)
+        b, c, h, w = x.shape
+        y = _empty_cl(b, c, 2 * h, 2 * w, x.dtype, x.device)
+        _lib.check(_lib.lib().y5_upsample2x(x.data_ptr(), xp, y.data_ptr(), c, b, h, w, c, _lib.dtype_code(x.dtype), _st(x.device)), "upsample2x")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy, dp = _nhwc(dy)
+        b, c, h2, w2 = dy.shape
+        dx = _empty_cl(b, c, h2 // 2, w2 // 2, dy.dtype, dy.device)
+        _lib.check(_lib.lib().y5_upsample2x_bwd(dy.data_ptr(), dp, dx.data_ptr(), c, b, h2 // 2, w2 // 2, c, _lib.dtype_code(dy.dtype),
+                                                _st(dy.device)), "upsample2x_bwd")
+        return dx
+
+
+class _SppfPoolCat(torch.autograd.Function):
+    """cat(a, m(a), m(m(a)), m(m(m(a)))) of SPPF (models/common.py:338-340), m = MaxPool2d(k, 1, k//2): one pooling launch
+    writes the three pooled slices next to a copy of `a`; the backward routes gradients through the arg-max chain."""
+
+    @staticmethod
+    def forward(ctx, a, k):
+        lib = _lib.lib()
+        a, ap = _nhwc(a)
+        b, c, h, w = a.shape
+        code = _lib.dtype_code(a.dtype)
+        cat = _empty_cl(b, 4 * c, h, w, a.dtype, a.device)
+        es = cat.element_size()
+        _lib.check(lib.y5_copy_view(a.data_ptr(), ap, cat.data_ptr(), 4 * c, b * h * w, c, code, _st(a.device)), "copy_view")
+        _lib.check(lib.y5_sppf_pool(a.data_ptr(), ap, cat.data_ptr() + c * es, cat.data_ptr() + 2 * c * es, cat.data_ptr() + 3 * c * es, 4 * c,
+                                    b, h, w, c, k, code, _st(a.device)), "sppf_pool")
+        ctx.save_for_backward(cat)
+        ctx.k = k
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        lib = _lib.lib()
+        (cat,) = ctx.saved_tensors
+        b, c4, h, w = cat.shape
+        c = c4 // 4
+        dcat, dp = _nhwc(dcat)
+        da = _empty_cl(b, c, h, w, cat.dtype, cat.device)
+        ws = torch.empty(3 * b * h * w * c, dtype=torch.float32, device=cat.device)
+        _lib.check(lib.y5_sppf_pool_bwd(cat.data_ptr(), c4, dcat.data_ptr(), dp, da.data_ptr(), c, b, h, w, c, ctx.k, _lib.dtype_code(cat.dtype),
+                                        ws.data_ptr(), _st(cat.device)), "sppf_pool_bwd")
+        return da, None
+
+
+class _Concat(torch.autograd.Function):
+    """Channel concat (models/common.py:453) as strided slice copies; the backward hands out channel-slice views of the
+    incoming gradient, which the consumers' kernels read in place through their pitch argument."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        lib = _lib.lib()
+        b, _, h, w = xs[0].shape
+        cs = [x.shape[1] for x in xs]
+        if any(c % 8 for c in cs):
+            raise NotImplementedError(f"y5b200: concat of channel counts {cs} (multiples of 8 only)")
+        out = _empty_cl(b, sum(cs), h, w, xs[0].dtype, xs[0].device)
+        es, off = out.element_size(), 0
+        for x, c in zip(xs, cs):
+            x, xp = _nhwc(x)
+            _lib.check(lib.y5_copy_view(x.data_ptr(), xp, out.data_ptr() + off * es, out.shape[1], b * h * w, c, _lib.dtype_code(out.dtype),
+                                        _st(out.device)), "copy_view")
+            off += c
+        ctx.cs = cs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        outs, off = [], 0
+        for c in ctx.cs:
+            outs.append(dout[:, off : off + c])
+            off += c
+        return tuple(outs)
 
 
 def stem_input(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -409,29 +498,26 @@ def _run(m, x, dt):
 
     if isinstance(m, mc.Conv):
         return conv_module(m, x)
-    if isinstance(m, mc.Bottleneck):
-        y = conv_module(m.cv2, conv_module(m.cv1, x))
-        return x + y if m.add else y
+    if isinstance(m, mc.Bottleneck):  # the shortcut add rides on cv2's normalise+activate pass
+        return conv_module(m.cv2, conv_module(m.cv1, x), residual=x if m.add else None)
     if isinstance(m, mc.C3):
         a = conv_module(m.cv1, x)
         for bt in m.m:
             a = _run(bt, a, dt)
-        return conv_module(m.cv3, torch.cat((a, conv_module(m.cv2, x)), 1))
+        return conv_module(m.cv3, _Concat.apply(a, conv_module(m.cv2, x)))
     if isinstance(m, mc.SPPF):
-        a = conv_module(m.cv1, x)
         k = m.m.kernel_size if isinstance(m.m.kernel_size, int) else m.m.kernel_size[0]
-        y1 = F.max_pool2d(a, k, 1, k // 2)
-        y2 = F.max_pool2d(y1, k, 1, k // 2)
-        y3 = F.max_pool2d(y2, k, 1, k // 2)
-        return conv_module(m.cv2, torch.cat((a, y1, y2, y3), 1))
+        return conv_module(m.cv2, _SppfPoolCat.apply(conv_module(m.cv1, x), k))
     if isinstance(m, torch.nn.Upsample):
-        return F.interpolate(x, scale_factor=m.scale_factor, mode=m.mode)
+        if float(m.scale_factor) != 2.0 or m.mode != "nearest":
+            raise NotImplementedError("y5b200: only nn.Upsample(scale_factor=2, mode='nearest')")
+        return _Upsample2x.apply(x)
     if isinstance(m, mc.Concat):
-        return torch.cat(x, m.d)
+        if m.d != 1:
+            raise NotImplementedError("y5b200: Concat along a dimension other than channels")
+        return _Concat.apply(*x)
     if isinstance(m, mc.Proto):
-        a = conv_module(m.cv1, x)
-        a = F.interpolate(a, scale_factor=2.0, mode="nearest")
-        return conv_module(m.cv3, conv_module(m.cv2, a))
+        return conv_module(m.cv3, conv_module(m.cv2, _Upsample2x.apply(conv_module(m.cv1, x))))
     if isinstance(m, torch.nn.Sequential):
         for sub in m:
             x = _run(sub, x, dt)
