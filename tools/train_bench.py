@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--skip-reference", action="store_true")
+    ap.add_argument("--train-only", action="store_true", help="skip the forward-only leg (for ncu launch lists of the step)")
     ap.add_argument("--graph", action="store_true", help="also time both arms with the whole step captured in a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="print the engine arm's top CUDA kernels (torch profiler)")
     a = ap.parse_args()
@@ -85,7 +86,7 @@ def main():
             m(img)
 
     t_step = timed(step_engine, a.steps)
-    t_fwd = timed(fwd_engine, a.steps)
+    t_fwd = float("nan") if a.train_only else timed(fwd_engine, a.steps)
     print(f"engine   {a.model} bs{a.batch} {a.size} {a.dtype}: step {t_step:.2f} ms ({a.batch / t_step * 1e3:.0f} img/s), forward only {t_fwd:.2f} ms")
     if a.graph:
         t_g = graphed(step_engine, a.steps)
