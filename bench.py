@@ -41,6 +41,7 @@ WORKLOADS = {  # name -> (model, per-GPU batch, image size, dtype)
     "yolov5n": ("yolov5n", 32, 640, "fp16"),
     "yolov5m": ("yolov5m", 32, 640, "fp16"),
     "yolov5x": ("yolov5x", 16, 640, "fp16"),
+    "yolov5x-seg-1280": ("yolov5x-seg", 2, 1280, "fp16"),  # BASELINE.json configs[4]: 16 images total = 2 per GPU at 8 GPUs
     # training step (BASELINE.json configs[3]: yolov5m, 128 images total = 16 per GPU at 8 GPUs, AMP): forward with
     # batch-statistics BN + ComputeLoss + backward + SGD step; N > 1 adds DDP's gradient all-reduce (the path's collective)
     "yolov5m-train": ("yolov5m", 16, 640, "fp16"),
@@ -441,10 +442,12 @@ def main():
 
     from yolov5_b200 import _lib
     from yolov5_b200.cfg import model_cfg
-    from yolov5_b200.models.yolo import DetectionModel
+    from yolov5_b200.models.yolo import DetectionModel, SegmentationModel
     from yolov5_b200.parallel import aggregate_throughput
     from yolov5_b200.utils.general import nms_device, non_max_suppression
 
+    seg = model_name.endswith("-seg")
+    nms_kw = dict(NMS_KW, nm=32) if seg else dict(NMS_KW)
     assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -461,7 +464,7 @@ def main():
 
     cfg = model_cfg(model_name)
     sd = bench_state_dict(cfg, seed=0)
-    model = DetectionModel(model_name)
+    model = (SegmentationModel if seg else DetectionModel)(model_name)
     model.load_state_dict(sd)
     model = model.to(dev, TDT[dt]).eval()
     n_rot = 3  # rotating inputs: 3 x batch > L2 (126 MB) for bs=32 fp16 (236 MB); each step also streams GBs of activations
@@ -469,8 +472,8 @@ def main():
     dev_in = [(h.to(dev).to(TDT[dt]) / 255) for h in host_u8]
 
     def step(x):
-        z, _ = model(x)
-        return nms_device(z, **NMS_KW)  # device-side result (rows, idx, count): no host sync inside `value`
+        z = model(x)[0]
+        return nms_device(z, **nms_kw)  # device-side result (rows, idx, count): no host sync inside `value`
 
     for i in range(a.warmup):
         out = step(dev_in[i % n_rot])
@@ -500,7 +503,7 @@ def main():
     # ---------------- e2e: pinned host uint8 in, detections out, per step, copy/compute overlapped ----------------
     copy_s = torch.cuda.Stream(dev)
     main_s = torch.cuda.current_stream(dev)
-    host_out = torch.empty(bs, NMS_KW["max_det"], 6, dtype=torch.float32).pin_memory()
+    host_out = torch.empty(bs, NMS_KW["max_det"], 6 + (32 if seg else 0), dtype=torch.float32).pin_memory()
     host_cnt = torch.empty(bs, dtype=torch.int32).pin_memory()
     stage = [torch.empty(bs, 3, size, size, dtype=torch.uint8, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -517,9 +520,9 @@ def main():
             if i >= 1:  # compute batch i-1
                 j = (i - 1) % 2
                 main_s.wait_event(ready[j])
-                z, _ = model(stage[j])
+                z = model(stage[j])[0]
                 freed[j].record(main_s)
-                rows, _, cnt = nms_device(z, **NMS_KW)
+                rows, _, cnt = nms_device(z, **nms_kw)
                 host_out.copy_(rows, non_blocking=True)
                 host_cnt.copy_(cnt, non_blocking=True)
 
@@ -560,7 +563,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(a.workload)
-        hbm_bound = a.workload in ("yolov5n", "yolov5s", "yolov5m")  # AI below machine balance
+        hbm_bound = model_name in ("yolov5n", "yolov5s", "yolov5m")  # AI below machine balance
         roof = {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all Conv/C3/SPPF launches of one forward)",
                 "bound": "hbm" if hbm_bound else "tensor",
                 "achieved": gbs if hbm_bound else tfs, "peak": pk["hbm"] if hbm_bound else pk["tf_sust"],
@@ -574,11 +577,11 @@ def main():
     # ---------------- NMS us/img (second half of the metric) ----------------
     nms_us = None
     if rank == 0:
-        z, _ = model(dev_in[0])
+        z = model(dev_in[0])[0]
         torch.cuda.synchronize(dev)
         e0.record()
         for _ in range(10):
-            nms_device(z, **NMS_KW)
+            nms_device(z, **nms_kw)
         e1.record()
         torch.cuda.synchronize(dev)
         nms_us = 1e3 * e0.elapsed_time(e1) / 10 / bs

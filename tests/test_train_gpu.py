@@ -298,3 +298,33 @@ def test_model_training_step_yolov5n(cuda, dtype):
     assert len(ratios) > 150, summary
     assert worst[0] <= 2.5 and summary["median"] <= 1.25, summary
     assert summary["total_mine"] <= 1e-3 + 1.5 * summary["total_amp"], summary
+
+
+def test_segmentation_model_training_forward_backward(cuda):
+    """SegmentationModel.train(): returns ([raw maps], proto) like models/yolo.py:147-150 in training; every parameter
+    (Proto branch and mask-coefficient columns included) receives a finite gradient, outputs match the torch oracle."""
+    from yolov5_b200.models.yolo import SegmentationModel
+
+    cfg = model_cfg("yolov5n-seg")
+    sd = model_ref.synth_state_dict(cfg, seed=41)
+    g = torch.Generator().manual_seed(42)
+    img = (torch.rand(4, 3, 128, 160, generator=g) * 255).to(torch.uint8)
+    m = SegmentationModel("yolov5n-seg")
+    m.load_state_dict(sd)
+    m = m.to(cuda).train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        outs, proto = m(img.to(cuda))
+    params = {k: v.to(cuda) for k, v in sd.items()}
+    with torch.no_grad():
+        x = img.to(cuda).float() / 255
+        r_outs, r_proto = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            l_outs, l_proto = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+    assert [tuple(o.shape) for o in outs] == [tuple(o.shape) for o in r_outs] and tuple(proto.shape) == tuple(r_proto.shape)
+    for a, r, lo in list(zip(outs, r_outs, l_outs)) + [(proto, r_proto, l_proto)]:
+        sc = float(r.abs().max())
+        e, el = float((a.detach().float() - r).abs().max()), float((lo.float() - r).abs().max())
+        assert e <= 1e-3 * sc + 2.0 * el, (e / sc, el / sc)
+    (sum(o.float().pow(2).mean() for o in outs) + proto.float().pow(2).mean()).backward()
+    missing = [k for k, q in m.named_parameters() if q.grad is None or not bool(torch.isfinite(q.grad).all())]
+    assert not missing, missing[:5]
