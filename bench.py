@@ -296,29 +296,26 @@ def train_main(a, rank, world, local):
     barrier()
     e2e_images, e2e_ms = aggregate_throughput(bs * a.steps, e0.elapsed_time(e1), dev)
 
-    # whole step in one CUDA graph (N = 1): what the kernels cost once Python / launch latency is out of the way
+    # whole step replayed from one CUDA graph through the public helper (N = 1): pinned host images + labels in, loss
+    # items out, every step -- what the kernels cost once Python / launch-issue time is out of the way
     graphed = tc_ref = None
     if rank == 0 and world == 1:
         try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                step(dev_img[0], dev_tgt[0])
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step(dev_img[0], dev_tgt[0])
-            g.replay()
+            from yolov5_b200.utils.torch_utils import GraphedTrainStep
+
+            gstep = GraphedTrainStep(model, loss_fn, opt, batch=bs, size=size, amp_dtype=tdt, max_norm=10.0)
+            for i in range(2):
+                host_items.copy_(gstep(host_img[i % n_rot], host_tgt[i % n_rot]), non_blocking=True)
             torch.cuda.synchronize(dev)
             e0.record()
-            for _ in range(a.steps):
-                g.replay()
+            for i in range(a.steps):
+                host_items.copy_(gstep(host_img[i % n_rot], host_tgt[i % n_rot]), non_blocking=True)
             e1.record()
             torch.cuda.synchronize(dev)
             graphed = {"value": bs * a.steps / (e0.elapsed_time(e1) / 1e3), "unit": "images/s",
-                       "what": "same step (fixed batch) captured once in a CUDA graph and replayed"}
-            del g
+                       "what": "yolov5_b200.utils.torch_utils.GraphedTrainStep: the same step captured once in a CUDA graph, replayed per "
+                               "batch with pinned-host uint8 images + labels uploaded and loss items downloaded every step"}
+            del gstep
         except Exception as ex:  # noqa: BLE001
             graphed = {"unavailable": repr(ex)[:200]}
     if rank == 0:

@@ -328,3 +328,48 @@ def test_segmentation_model_training_forward_backward(cuda):
     (sum(o.float().pow(2).mean() for o in outs) + proto.float().pow(2).mean()).backward()
     missing = [k for k, q in m.named_parameters() if q.grad is None or not bool(torch.isfinite(q.grad).all())]
     assert not missing, missing[:5]
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """utils.torch_utils.GraphedTrainStep (whole step in one CUDA graph, labels padded with zero-size boxes) must walk
+    the weights like the eager loop does."""
+    from yolov5_b200.utils.torch_utils import GraphedTrainStep
+
+    cfg = model_cfg("yolov5n")
+    sd = model_ref.synth_state_dict(cfg, seed=51)
+    g = torch.Generator().manual_seed(52)
+    batches = [((torch.rand(2, 3, 64, 64, generator=g) * 255).to(torch.uint8).to(cuda),
+                torch.from_numpy(loss_ref.synth_targets(2, seed=60 + i)).float().to(cuda)) for i in range(3)]
+
+    def make():
+        m = DetectionModel("yolov5n")
+        m.load_state_dict(sd)
+        m = m.to(cuda).train()
+        m.hyp = dict(HYP_SCRATCH_LOW)
+        return m, ComputeLoss(m), torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
+
+    m1, loss1, opt1 = make()
+    items_eager = []
+    for img, tgt in batches:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            p = m1(img)
+        loss, items = loss1(p, tgt)
+        opt1.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), max_norm=10.0)
+        opt1.step()
+        items_eager.append(items.clone())
+    m2, loss2, opt2 = make()
+    step = GraphedTrainStep(m2, loss2, opt2, batch=2, size=64, max_targets=96, amp_dtype=torch.bfloat16)
+    for (img, tgt), ie in zip(batches, items_eager):
+        ig = step(img, tgt).clone()
+        assert torch.allclose(ig, ie, rtol=2e-2, atol=1e-4), (ig, ie)
+    torch.cuda.synchronize()
+    w1 = torch.cat([q.detach().flatten() for q in m1.parameters()])
+    w2 = torch.cat([q.detach().flatten() for q in m2.parameters()])
+    w0 = torch.cat([sd[k].flatten() for k, _ in m1.named_parameters()]).to(cuda)
+    moved = float((w1 - w0).norm())
+    assert moved > 0 and float((w1 - w2).norm()) <= 0.1 * moved, (float((w1 - w2).norm()), moved)  # bf16 noise + atomics order
+    rm1 = m1.model[0].bn.running_mean
+    assert torch.allclose(rm1, m2.model[0].bn.running_mean, rtol=1e-2, atol=1e-4)
+    assert int(m2.model[0].bn.num_batches_tracked) == 3
