@@ -36,6 +36,21 @@ def test_library_is_sm100a_with_tcgen05_and_tma(built_lib):
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.4D.IM2COL"):  # tcgen05.mma, TMA, tcgen05.ld, im2col TMA
         assert mnemonic in sass, mnemonic
+    # the weight-gradient kernel is a tcgen05 kernel of its own (MN-major operands) with vector fp32 reductions
+    wg = sass[sass.index("conv_wgrad_kernel"):]
+    wg = wg[: wg.index("Function :", 10)] if "Function :" in wg[10:] else wg
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "REDG.E.ADD.F32x4"):
+        assert mnemonic in wg, mnemonic
+
+
+def test_wgrad_and_bn_argument_validation_without_gpu(built_lib):
+    lib = built_lib
+    d = _lib.WgradDesc()
+    assert lib.y5_conv_wgrad(ctypes.byref(d), None) == -1 and b"null" in lib.y5_last_error()
+    assert lib.y5_bn_workspace_bytes(64) == 64 * 2 * 8
+    assert lib.y5_sppf_bwd_workspace_bytes(2, 20, 20, 128) == 3 * 2 * 20 * 20 * 128 * 4
+    assert lib.y5_bn_stats(None, 64, 10, 64, _lib.Y5_F16, None, None) == -1
+    assert lib.y5_weight_pack(None, _lib.Y5_F32, 8, 8, 1, None, 8, None, 8, _lib.Y5_F16, None) == -1
 
 
 def test_argument_validation_without_gpu(built_lib):

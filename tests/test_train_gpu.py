@@ -373,3 +373,20 @@ def test_graphed_train_step_matches_eager(cuda):
     rm1 = m1.model[0].bn.running_mean
     assert torch.allclose(rm1, m2.model[0].bn.running_mean, rtol=1e-2, atol=1e-4)
     assert int(m2.model[0].bn.num_batches_tracked) == 3
+
+
+def test_training_with_a_model_cast_to_bf16(cuda):
+    """No autocast: model.bfloat16().train() -- parameters, BN affine terms and running statistics are bf16 tensors; the
+    kernels work on fp32 copies of the small vectors and gradients come back in the parameter dtype."""
+    cfg = model_cfg("yolov5n")
+    m = DetectionModel("yolov5n")
+    m.load_state_dict(model_ref.synth_state_dict(cfg, seed=61))
+    m = m.to(cuda).bfloat16().train()
+    img = (torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(62)) * 255).to(torch.uint8).to(cuda)
+    p = m(img)
+    assert all(q.dtype == torch.bfloat16 for q in p)
+    sum(q.float().pow(2).mean() for q in p).backward()
+    for k, q in m.named_parameters():
+        assert q.grad is not None and q.grad.dtype == torch.bfloat16 and bool(torch.isfinite(q.grad).all()), k
+    bn = m.model[0].bn
+    assert bn.running_mean.dtype == torch.bfloat16 and float(bn.running_mean.float().abs().sum()) > 0

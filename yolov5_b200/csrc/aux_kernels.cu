@@ -169,6 +169,8 @@ __global__ void sppf_pool_smem_kernel(const uint16_t* __restrict__ x, int x_pitc
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint16_t* __restrict__ x, int x_pitch, uint16_t* __restrict__ y, int y_pitch, int B,
                                   int H, int W, int C) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const int cv = C >> 3;
     const int Ho = 2 * H, Wo = 2 * W;
     const long long total = static_cast<long long>(B) * Ho * Wo * cv;
@@ -187,6 +189,8 @@ __global__ void upsample2x_kernel(const uint16_t* __restrict__ x, int x_pitch, u
 
 __global__ void copy_view_kernel(const uint16_t* __restrict__ x, int x_pitch, uint16_t* __restrict__ y, int y_pitch,
                                  long long pixels, int C) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const int cv = C >> 3;
     const long long total = pixels * cv;
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -279,7 +283,7 @@ extern "C" Y5_API int y5_upsample2x(const void* x, int32_t x_pitch, void* y, int
     if (c % 8 || x_pitch % 8 || y_pitch % 8 || !half_dtype(dtype)) return set_error(Y5_E_UNSUPPORTED, "upsample2x: c/pitch %% 8, fp16/bf16 only");
     const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
     const int threads = 256, grid = grid_for(total, threads);
-    upsample2x_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), x_pitch,
+    launch_pdl(upsample2x_kernel, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(x), x_pitch,
                                                                                 static_cast<uint16_t*>(y), y_pitch, batch, h, w, c);
     return check_launch("upsample2x");
 }
@@ -290,7 +294,7 @@ extern "C" Y5_API int y5_copy_view(const void* x, int32_t x_pitch, void* y, int3
     if (c % 8 || x_pitch % 8 || y_pitch % 8 || !half_dtype(dtype)) return set_error(Y5_E_UNSUPPORTED, "copy_view: c/pitch %% 8, fp16/bf16 only");
     const long long total = pixels * (c / 8);
     const int threads = 256, grid = grid_for(total, threads);
-    copy_view_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), x_pitch,
+    launch_pdl(copy_view_kernel, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(x), x_pitch,
                                                                                static_cast<uint16_t*>(y), y_pitch, pixels, c);
     return check_launch("copy_view");
 }

@@ -76,6 +76,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_wait();  // PDL: barrier init / TMEM allocation above overlap the predecessor's tail
+    griddep_launch_dependents();
 
     // work item
     int t = blockIdx.x;
@@ -303,7 +305,7 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
     if (attr_err != cudaSuccess) return set_error(int(attr_err), "wgrad: cudaFuncSetAttribute failed");
     const long long grid = items * p.splits;
     count_launch();
-    conv_wgrad_kernel<<<static_cast<unsigned>(grid), kWgThreads, smem, st>>>(tmDy, tmX, p);
+    launch_pdl(conv_wgrad_kernel, dim3(static_cast<unsigned>(grid)), dim3(kWgThreads), smem, st, tmDy, tmX, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(int(e), "wgrad launch failed: %s", cudaGetErrorString(e));
     return 0;

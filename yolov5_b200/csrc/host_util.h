@@ -4,7 +4,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 namespace y5 {
+
+// Launch with the programmatic-dependent-launch attribute: the kernel may be scheduled while its predecessor in the
+// stream drains (every such kernel starts with griddepcontrol.wait, which blocks until the predecessor has completed and
+// flushed, then griddepcontrol.launch_dependents).  Y5_PDL=0 turns the attribute off.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("Y5_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // records a thread-local message retrievable through y5_last_error(); returns `code`
 int set_error(int code, const char* fmt, ...);

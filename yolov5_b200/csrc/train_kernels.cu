@@ -83,6 +83,8 @@ __device__ __forceinline__ void block_publish(float (&acc)[NV][8], int cgx, int 
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads) col_stats_kernel(const void* __restrict__ y, int pitch, long long rows, int channels, int bf16,
                                                                 int cgx, int rpb, double* __restrict__ ws) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* 
                                                                     const double* __restrict__ sums, float eps, float momentum,
                                                                     float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                     const void* __restrict__ res, int res_pitch) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
@@ -212,6 +216,8 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const
                                                                            int cgx, int rpb, const float* __restrict__ mean,
                                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                            const float* __restrict__ beta, double* __restrict__ ws) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
@@ -268,6 +274,8 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
                                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                           const double* __restrict__ ws, float* __restrict__ dgamma,
                                                                           float* __restrict__ dbeta) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     __shared__ ChanConst cc[256];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
@@ -323,6 +331,8 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
 // stride-1 conv over the stuffed tensor
 __global__ void zero_stuff2x_kernel(const uint4* __restrict__ in, int in_pitch16, uint4* __restrict__ out, int out_pitch16, int batch, int h,
                                     int w, int c16) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const long long total = static_cast<long long>(batch) * (2 * h) * (2 * w) * c16;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int cc = static_cast<int>(i % c16);
@@ -346,6 +356,8 @@ __device__ __forceinline__ float load_w(const void* w, long long i, int src_dtyp
 }
 __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, int cout, int cin, int k, uint16_t* __restrict__ fwd, int ci_pad,
                                    uint16_t* __restrict__ dgrad, int co_pad, int bf16) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const long long n_fwd = fwd ? static_cast<long long>(cout) * k * k * ci_pad : 0;
     const long long n_dg = dgrad ? static_cast<long long>(cin) * k * k * co_pad : 0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_fwd + n_dg;
@@ -376,6 +388,8 @@ __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, in
 // backward of nn.Upsample(scale_factor=2, 'nearest'): dx[n,y,x,:] = sum of the 2x2 block of dy (fp32 sum, one rounding)
 __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, int dy_pitch, void* __restrict__ dx, int dx_pitch, int B, int H, int W, int C,
                                       int bf16) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
     const int cv = C >> 3;
     const long long total = static_cast<long long>(B) * H * W * cv;
     const bool b = bf16 != 0;
@@ -478,7 +492,7 @@ extern "C" Y5_API int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, in
     if (!workspace || rows <= 0) return set_error(Y5_E_INVALID, "bn_stats: bad argument");
     const RowGeom g = row_geom(channels, rows, 3);
     count_launch();
-    col_stats_kernel<0><<<row_grid(g, channels, rows), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(col_stats_kernel<0>, row_grid(g, channels, rows), dim3(kRedThreads), 0, static_cast<cudaStream_t>(stream), 
         y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb, static_cast<double*>(workspace));
     return launch_status("bn_stats");
 }
@@ -492,7 +506,7 @@ extern "C" Y5_API int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int
     cudaMemsetAsync(workspace, 0, static_cast<size_t>(channels) * sizeof(double), st);
     const RowGeom g = row_geom(channels, rows, 3);
     count_launch(2);
-    col_stats_kernel<1><<<row_grid(g, channels, rows), kRedThreads, 0, st>>>(y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb,
+    launch_pdl(col_stats_kernel<1>, row_grid(g, channels, rows), dim3(kRedThreads), 0, st, y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb,
                                                                               static_cast<double*>(workspace));
     col_sum_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<const double*>(workspace), channels, out);
     return launch_status("col_sum");
@@ -510,7 +524,7 @@ extern "C" Y5_API int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int
         if (int e = check_view(residual, res_pitch, channels, "bn_act_fwd residual")) return e;
     const RowGeom g = row_geom(channels, rows, 6);
     count_launch();
-    bn_act_fwd_kernel<<<row_grid(g, channels, rows), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(bn_act_fwd_kernel, row_grid(g, channels, rows), dim3(kRedThreads), 0, static_cast<cudaStream_t>(stream), 
         y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<const double*>(sums), eps, momentum,
         running_mean, running_var, residual, res_pitch);
     return launch_status("bn_act_fwd");
@@ -529,9 +543,9 @@ extern "C" Y5_API int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* 
     const RowGeom g = row_geom(channels, rows, 3), ga = row_geom(channels, rows, 6);
     const dim3 grid = row_grid(g, channels, rows);
     count_launch(2);
-    bn_act_bwd_reduce_kernel<<<grid, kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd,
+    launch_pdl(bn_act_bwd_reduce_kernel, grid, dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd,
                                                            gamma, beta, static_cast<double*>(workspace));
-    bn_act_bwd_apply_kernel<<<row_grid(ga, channels, rows), kRedThreads, 0, st>>>(y, y_pitch, dz, dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, act, ga.cgx, ga.rpb,
+    launch_pdl(bn_act_bwd_apply_kernel, row_grid(ga, channels, rows), dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, act, ga.cgx, ga.rpb,
                                                           mean, invstd, gamma, beta, static_cast<const double*>(workspace), dgamma, dbeta);
     return launch_status("bn_act_bwd");
 }
@@ -545,7 +559,7 @@ extern "C" Y5_API int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, i
     const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
     count_launch();
-    zero_stuff2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), x_pitch / 8, static_cast<uint4*>(y),
+    launch_pdl(zero_stuff2x_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), x_pitch / 8, static_cast<uint4*>(y),
                                                                                y_pitch / 8, batch, h, w, c / 8);
     return launch_status("zero_stuff2x");
 }
@@ -561,7 +575,7 @@ extern "C" Y5_API int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out
                             (dgrad ? static_cast<long long>(in_c) * ksize * ksize * out_c_pad : 0);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
     count_launch();
-    weight_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_dtype, out_c, in_c, ksize, static_cast<uint16_t*>(fwd), in_c_pad,
+    launch_pdl(weight_pack_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), w, w_dtype, out_c, in_c, ksize, static_cast<uint16_t*>(fwd), in_c_pad,
                                                                               static_cast<uint16_t*>(dgrad), out_c_pad, dtype == Y5_BF16);
     return launch_status("weight_pack");
 }
@@ -575,7 +589,7 @@ extern "C" Y5_API int y5_upsample2x_bwd(const void* dy, int32_t dy_pitch, void* 
     const long long total = static_cast<long long>(batch) * h * w * (c / 8);
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
     count_launch();
-    upsample2x_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dy_pitch, dx, dx_pitch, batch, h, w, c, dtype == Y5_BF16);
+    launch_pdl(upsample2x_bwd_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), dy, dy_pitch, dx, dx_pitch, batch, h, w, c, dtype == Y5_BF16);
     return launch_status("upsample2x_bwd");
 }
 
