@@ -7,6 +7,8 @@ reference's key names* plus the model dict, so the very same weights can be fed 
 
 Pinned: tests/golden/model_*.npz hold outputs of the real reference (imported through
 tests/golden/refshim.py) for seeded weights/inputs; tests/test_oracle_golden.py checks this file against them.
+The training-mode forward (``bn_batch_stats=True``: BatchNorm with batch statistics, models/common.py:86-88 under
+model.train()) is pinned the same way by tests/golden/train_step.npz (reference forward + ComputeLoss + backward).
 
 Reference lines restated (paths relative to /root/reference):
   models/common.py:62-92     autopad, Conv (conv -> BN(eps 1e-3) -> SiLU)      -> conv_block

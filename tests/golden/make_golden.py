@@ -240,10 +240,55 @@ def gen_loss():
         store[f"{tag}.meta"] = np.array([bs, hw[0], hw[1], seed])
         print(f"loss {tag}: {loss.item():.6f} items {items.tolist()} matches {[len(d['b']) for d in bt]}; oracle == reference")
     np.savez_compressed(f"{HERE}/loss.npz", **store)
+def gen_train():
+    """Training-mode pin: the real reference in model.train() -- forward with batch-statistics BatchNorm (models/common.py:
+    86-88), ComputeLoss, backward -- against the oracle's bn_batch_stats forward + loss_ref on the same seeded weights,
+    images and labels: raw head maps, loss, BN running-statistic updates and parameter gradients."""
+    from utils.loss import ComputeLoss
+
+    from oracle import loss_ref
+    from yolov5_b200.cfg import HYP_SCRATCH_LOW
+
+    name, shape, seed = "yolov5n", (4, 3, 128, 128), 30
+    cfg = model_cfg(name)
+    sd = model_ref.synth_state_dict(cfg, seed=seed)
+    m = ref_model(name, sd).train()
+    m.hyp = dict(HYP_SCRATCH_LOW)
+    x = synth_image(shape, seed + 100)
+    targets = torch.from_numpy(loss_ref.synth_targets(shape[0], seed=seed + 200))
+    p_ref = m(x)
+    loss_r, items_r = ComputeLoss(m)(p_ref, targets)
+    loss_r.backward()
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "anchors" not in k) for k, v in sd.items()}
+    p_orc = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+    loss_o, items_o = loss_ref.compute_loss(p_orc, targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)
+    loss_o.backward()
+    store = {"shape": np.array(shape), "seed": np.array([seed, seed + 100, seed + 200])}
+    for l, (a, b) in enumerate(zip(p_ref, p_orc)):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-4), (l, (a - b).abs().max())
+        store[f"raw{l}"] = a.detach().numpy()
+    assert torch.allclose(loss_r, loss_o, rtol=1e-5, atol=1e-6), (loss_r, loss_o)
+    store["loss"] = loss_r.detach().numpy()
+    store["items"] = items_r.detach().numpy()
+    worst = 0.0
+    for k, q in m.named_parameters():
+        g_r, g_o = q.grad, params[k].grad
+        assert g_o is not None, k
+        err = float((g_r - g_o).abs().max() / (g_r.abs().max() + 1e-12))
+        worst = max(worst, err)
+        assert err < 1e-3, (k, err)
+        store[f"gnorm.{k}"] = np.array([float(g_r.norm()), float(g_r.abs().max())])
+    for k in ("model.0.conv.weight", "model.0.bn.weight", "model.9.cv2.conv.weight", "model.24.m.0.weight", "model.24.m.2.bias"):
+        store[f"grad.{k}"] = dict(m.named_parameters())[k].grad.numpy()
+    # running statistics after one training forward (momentum 0.03, unbiased variance)
+    for k in ("model.0.bn.running_mean", "model.0.bn.running_var", "model.8.cv3.bn.running_var"):
+        store[f"stat.{k}"] = m.state_dict()[k].numpy()
+    print(f"train: loss {float(loss_r):.6f}, max rel grad diff ref-oracle {worst:.2e} over {len(list(m.parameters()))} tensors")
+    np.savez_compressed(f"{HERE}/train_step.npz", **store)
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg", "model", "nms", "loss"]
+    which = sys.argv[1:] or ["cfg", "model", "nms", "loss", "train"]
     for w in which:
-        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss}[w]()
+        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss, "train": gen_train}[w]()
     print("golden fixtures written to", HERE)

@@ -117,3 +117,35 @@ def test_loss_oracle_vs_golden():
         gs = np.array([[t.grad.double().sum().item(), t.grad.double().abs().sum().item()] for t in p])
         np.testing.assert_allclose(gs[:, 1], g[f"{tag}.gradsum"][:, 1], rtol=1e-4)
         np.testing.assert_allclose(p[0].grad.numpy().reshape(-1)[::1009], g[f"{tag}.grad_sample0"], rtol=1e-4, atol=1e-8)
+
+
+def test_oracle_training_step_matches_reference_fixture():
+    """tests/golden/train_step.npz holds the REAL reference's model.train() forward (batch-statistics BN), ComputeLoss,
+    backward and BN running-statistic update (generated by tests/golden/make_golden.py train).  The oracle's
+    bn_batch_stats forward + loss_ref + torch autograd must reproduce them."""
+    import numpy as np
+    import torch
+
+    from oracle import loss_ref, model_ref
+    from yolov5_b200.cfg import HYP_SCRATCH_LOW, model_cfg
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step.npz"))
+    shape, (seed, seed_x, seed_t) = tuple(int(v) for v in g["shape"]), (int(v) for v in g["seed"])
+    cfg = model_cfg("yolov5n")
+    sd = model_ref.synth_state_dict(cfg, seed=seed)
+    x = torch.from_numpy(np.random.RandomState(seed_x).uniform(0, 1, shape).astype(np.float32))
+    targets = torch.from_numpy(loss_ref.synth_targets(shape[0], seed=seed_t))
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "anchors" not in k) for k, v in sd.items()}
+    p = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
+    for l, q in enumerate(p):
+        assert np.allclose(q.detach().numpy(), g[f"raw{l}"], rtol=1e-4, atol=1e-4)
+    loss, items = loss_ref.compute_loss(p, targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)
+    assert np.allclose(loss.detach().numpy(), g["loss"], rtol=1e-5) and np.allclose(items.numpy(), g["items"], rtol=1e-5)
+    loss.backward()
+    for key in g.files:
+        if key.startswith("grad."):
+            ref = g[key]
+            got = params[key[5:]].grad.numpy()
+            assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max(), key
+        elif key.startswith("gnorm."):
+            assert abs(float(params[key[6:]].grad.norm()) - float(g[key][0])) <= 1e-3 * float(g[key][0]) + 1e-9, key

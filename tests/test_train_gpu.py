@@ -390,3 +390,43 @@ def test_training_with_a_model_cast_to_bf16(cuda):
         assert q.grad is not None and q.grad.dtype == torch.bfloat16 and bool(torch.isfinite(q.grad).all()), k
     bn = m.model[0].bn
     assert bn.running_mean.dtype == torch.bfloat16 and float(bn.running_mean.float().abs().sum()) > 0
+
+
+def test_training_step_against_the_real_reference_fixture(cuda):
+    """tests/golden/train_step.npz = the real reference's training step (fp32, CPU): the engine under fp16 autocast must
+    land within low-precision distance of it -- head maps, loss, BN running statistics, gradients."""
+    import os
+
+    import numpy as np
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step.npz"))
+    shape, (seed, seed_x, seed_t) = tuple(int(v) for v in g["shape"]), (int(v) for v in g["seed"])
+    cfg = model_cfg("yolov5n")
+    sd = model_ref.synth_state_dict(cfg, seed=seed)
+    x = torch.from_numpy(np.random.RandomState(seed_x).uniform(0, 1, shape).astype(np.float32))
+    targets = torch.from_numpy(loss_ref.synth_targets(shape[0], seed=seed_t)).float()
+    m = DetectionModel("yolov5n")
+    m.load_state_dict(sd)
+    m = m.to(cuda).train()
+    m.hyp = dict(HYP_SCRATCH_LOW)
+    with torch.autocast("cuda", dtype=torch.float16):
+        p = m(x.to(cuda))
+    for l, q in enumerate(p):
+        ref = torch.from_numpy(g[f"raw{l}"])
+        assert float((q.detach().float().cpu() - ref).abs().max()) <= 1e-2 * float(ref.abs().max()), l
+    loss, items = ComputeLoss(m)(p, targets.to(cuda))
+    assert abs(float(loss) - float(g["loss"][0])) <= 5e-3 * float(g["loss"][0])
+    loss.backward()
+    named = dict(m.named_parameters())
+    for key in g.files:
+        if key.startswith("grad."):
+            ref = torch.from_numpy(g[key])
+            got = named[key[5:]].grad.float().cpu()
+            assert float((got - ref).norm()) <= 0.2 * float(ref.norm()), (key, float((got - ref).norm() / ref.norm()))
+        elif key.startswith("stat."):
+            ref = torch.from_numpy(g[key])
+            got = m.state_dict()[key[5:]].float().cpu()
+            assert torch.allclose(got, ref, rtol=2e-2, atol=2e-3), key
+    tot = sum(float(g[k][0]) ** 2 for k in g.files if k.startswith("gnorm.")) ** 0.5
+    mine = sum(float(q.grad.float().norm()) ** 2 for q in m.parameters()) ** 0.5
+    assert abs(mine - tot) <= 0.05 * tot, (mine, tot)
