@@ -247,14 +247,16 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
     const int bn = p.n_blocks * 64;
     // taps per CTA: accumulators of a group share TMEM (512 columns); a 256-wide tile keeps one tap (its stage is
     // already 48 KB); groups are balanced (9 taps, limit 5 -> 5 + 4)
+    static const int g_cap = [] { const char* e = getenv("Y5_WG_GROUP_MAX"); return e && atoi(e) > 0 ? atoi(e) : 5; }();
+    static const unsigned stage_kb = [] { const char* e = getenv("Y5_WG_STAGE_KB"); return e && atoi(e) > 0 ? (unsigned)atoi(e) : 56u; }();
     int gmax = bn >= 256 ? 1 : 512 / bn;
-    if (gmax > 5) gmax = 5;
+    if (gmax > g_cap) gmax = g_cap;
     p.tap_groups = (p.taps + gmax - 1) / gmax;
     p.group = (p.taps + p.tap_groups - 1) / p.tap_groups;
     // pixels per stage: as many as keep a stage within ~56 KB (>= 3 stages in flight)
     p.pix = 64;
     for (int cand : {256, 128}) {
-        if (static_cast<uint32_t>(2 + p.group * p.n_blocks) * cand * 128u <= 56u * 1024u) { p.pix = cand; break; }
+        if (static_cast<uint32_t>(2 + p.group * p.n_blocks) * cand * 128u <= stage_kb * 1024u) { p.pix = cand; break; }
     }
     p.box_bytes = p.pix * 128u;
     p.kblocks = (p.M + p.pix - 1) / p.pix;

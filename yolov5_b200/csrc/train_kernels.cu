@@ -9,6 +9,7 @@
 // rounded to the activation dtype, SiLU on that rounded value, gradients rounded to the activation dtype between ops.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/y5b200.h"
 #include "common.cuh"
@@ -24,7 +25,14 @@ struct RowGeom {
     int rpb;   // tensor rows per block: sized so the grid has ~8 blocks per SM (small maps) but at most 1024 rows
 };
 constexpr int kUnroll = 4;  // rows per loop trip of the statistics pass; the BN passes take 2 and rely on occupancy
+static inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && atoi(e) > 0 ? atoi(e) : dflt;
+}
 static inline RowGeom row_geom(int channels, long long nrows, int blocks_per_sm) {
+    // tuning knobs (blocks per SM the grids aim for): reductions default 3, elementwise passes default 6
+    static const int red_bps = env_int("Y5_BN_RED_BPS", 3), elt_bps = env_int("Y5_BN_ELT_BPS", 6);
+    blocks_per_sm = blocks_per_sm <= 3 ? red_bps : elt_bps;
     const int cg = channels / 8;
     RowGeom g;
     g.cgx = cg >= 32 ? 32 : (cg >= 16 ? 16 : (cg >= 8 ? 8 : (cg >= 4 ? 4 : (cg >= 2 ? 2 : 1))));
