@@ -69,3 +69,46 @@ def test_argument_validation_without_gpu(built_lib):
     bk, bn = ctypes.c_int32(), ctypes.c_int32()
     assert lib.y5_conv_pick(128, 256, 51200, ctypes.byref(bk), ctypes.byref(bn)) == 0
     assert bk.value == 64 and bn.value in (128, 256)
+
+
+def _header_structs():
+    """{struct name: [field names in declaration order]} parsed from include/y5b200.h"""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef struct \w+ \{(.*?)\}\s*(\w+);", src, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names = [first.split()[-1]] + [r.strip() for r in rest]
+            fields += [re.sub(r"\[.*\]", "", n).lstrip("*").strip() for n in names]
+        out[name] = fields
+    return out
+
+
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """sizeof / offsetof of every struct in the header (compiled by gcc) == the ctypes mirrors in yolov5_b200/_lib.py."""
+    mirrors = {"y5_conv_desc": _lib.ConvDesc, "y5_detect_desc": _lib.DetectDesc, "y5_nms_params": _lib.NmsParams,
+               "y5_loss_params": _lib.LossParams, "y5_wgrad_desc": _lib.WgradDesc}
+    structs = _header_structs()
+    assert sorted(structs) == sorted(mirrors), (sorted(structs), sorted(mirrors))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for s, fields in structs.items():
+        lines.append(f'  printf("{s} %zu", sizeof({s}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({s}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    got = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in got:
+        name, size, *offs = line.split()
+        cls = mirrors[name]
+        assert int(size) == ctypes.sizeof(cls), (name, size, ctypes.sizeof(cls))
+        py = [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert [int(o) for o in offs] == py, (name, offs, py)
