@@ -226,6 +226,10 @@ typedef struct y5_wgrad_desc {
     int32_t dtype;        /* Y5_F16 | Y5_BF16 (x and dy) */
     int32_t accumulate;
     int32_t reserved;
+    /* optional, as in y5_conv_desc: kw != 0 -> filter is ksize x kw with horizontal padding pad_w (dweight is
+     * [out_c][ksize][kw][in_c]); non-zero strides (elements) describe a general NHWC view, e.g. overlapping "wide pixels" */
+    int32_t kw, pad_w;
+    int64_t in_x_stride, in_y_stride, in_n_stride;
 } y5_wgrad_desc;
 int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream);
 

@@ -82,6 +82,8 @@ class WgradDesc(C.Structure):
         ("dweight", C.c_void_p),
         ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
         ("dtype", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+        ("kw", C.c_int32), ("pad_w", C.c_int32),
+        ("in_x_stride", C.c_int64), ("in_y_stride", C.c_int64), ("in_n_stride", C.c_int64),
     ]
 
 

@@ -219,9 +219,15 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
     if ((d->in_pitch % 8) || (d->dout_pitch % 8) || (reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->dout) & 15) ||
         (reinterpret_cast<uintptr_t>(d->dweight) & 15))
         return set_error(Y5_E_INVALID, "wgrad: views must be 16-byte aligned with pitches that are multiples of 8 elements");
-    if (d->in_pitch < d->in_c || d->dout_pitch < d->out_c) return set_error(Y5_E_INVALID, "wgrad: pitch smaller than channel count");
-    const int k = d->ksize;
-    const int Ho = (d->in_h + 2 * d->pad - k) / d->stride + 1, Wo = (d->in_w + 2 * d->pad - k) / d->stride + 1;
+    const bool strided_view = d->in_x_stride || d->in_y_stride || d->in_n_stride;
+    if ((!strided_view && d->in_pitch < d->in_c) || d->dout_pitch < d->out_c)
+        return set_error(Y5_E_INVALID, "wgrad: pitch smaller than channel count");
+    if ((d->in_x_stride % 8) || (d->in_y_stride % 8) || (d->in_n_stride % 8) || d->kw < 0 || d->pad_w < 0)
+        return set_error(Y5_E_INVALID, "wgrad: strides must be multiples of 8 elements");
+    const int k = d->ksize;                       // filter rows
+    const int kw = d->kw ? d->kw : d->ksize;      // filter columns
+    const int pad_w = d->kw ? d->pad_w : d->pad;
+    const int Ho = (d->in_h + 2 * d->pad - k) / d->stride + 1, Wo = (d->in_w + 2 * pad_w - kw) / d->stride + 1;
     if (Ho <= 0 || Wo <= 0) return set_error(Y5_E_INVALID, "wgrad: empty output");
     const long long M = static_cast<long long>(d->batch) * Ho * Wo;
     if (M > 0x7fffffffLL) return set_error(Y5_E_UNSUPPORTED, "wgrad: too many pixels");
@@ -231,13 +237,15 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
     p.M = static_cast<int>(M);
     p.Cout = d->out_c;
     p.Cin = d->in_c;
-    p.kh = p.kw = k;
+    p.kh = k;
+    p.kw = kw;
     p.stride = d->stride;
-    p.pad_h = p.pad_w = d->pad;
+    p.pad_h = d->pad;
+    p.pad_w = pad_w;
     p.Wo = Wo;
     p.HoWo = Ho * Wo;
-    p.linear = (k == 1 && d->stride == 1 && d->pad == 0) ? 1 : 0;
-    p.taps = k * k;
+    p.linear = (k == 1 && kw == 1 && d->stride == 1 && d->pad == 0 && pad_w == 0 && !strided_view) ? 1 : 0;
+    p.taps = k * kw;
     const int blocks_total = (d->in_c + 63) / 64;
     p.n_blocks = blocks_total < 4 ? blocks_total : 4;
     p.ci_tiles = (blocks_total + p.n_blocks - 1) / p.n_blocks;
@@ -290,8 +298,10 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
         int e = encode_tiled(&tmX, d->dtype, d->in, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad X");
         if (e) return e;
     } else {
-        const long long xs = d->in_pitch, ys = xs * d->in_w, ns = ys * d->in_h;
-        int e = encode_im2col(&tmX, d->dtype, d->in, d->in_c, d->in_w, d->in_h, d->batch, xs, ys, ns, k, k, d->stride, d->pad, d->pad, 64,
+        const long long xs = d->in_x_stride ? d->in_x_stride : d->in_pitch;
+        const long long ys = d->in_y_stride ? d->in_y_stride : xs * d->in_w;
+        const long long ns = d->in_n_stride ? d->in_n_stride : ys * d->in_h;
+        int e = encode_im2col(&tmX, d->dtype, d->in, d->in_c, d->in_w, d->in_h, d->batch, xs, ys, ns, k, kw, d->stride, d->pad, pad_w, 64,
                               p.pix, CU_TENSOR_MAP_SWIZZLE_128B);
         if (e) return e;
     }

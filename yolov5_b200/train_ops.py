@@ -21,11 +21,13 @@ cast), BN statistics / affine gradients / weight gradients in fp32 -- the refere
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 from ._lib import ConvDesc, WgradDesc
+from .engine import pack_weight
 
 _CL = torch.channels_last
 
@@ -177,6 +179,60 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, s: int, p: int) -> tor
     return dw.permute(0, 3, 1, 2).contiguous()  # gradients must be laid out like the parameter (DDP buckets, optimizers)
 
 
+def stem_wide_enabled() -> bool:
+    """Stem as a 3x1 conv over overlapping 48-channel "wide pixels" of the zero-padded space-to-depth image (the form the
+    inference engine uses): 3 TMA rows per pixel instead of 9 for the forward and the weight gradient, which are bound by
+    the TMA row rate on this 16-channel input.  Opt-in (Y5_TRAIN_STEM_WIDE=1) until it has been measured on a B200."""
+    return os.environ.get("Y5_TRAIN_STEM_WIDE", "0") == "1"
+
+
+def _wide_geom(buf: torch.Tensor):
+    b, h2, wp, _ = buf.shape  # (B, H/2, W/2 + 2, 16): one zero cell left and right of every row
+    return b, h2, wp - 2, dict(x=16, y=wp * 16, n=h2 * wp * 16)
+
+
+def stem_conv_wide(buf: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
+    """y = conv3x3/s1/p1(s2d image, w3) evaluated as a 3x1 conv over 48-channel wide pixels.  w3: (O,16,3,3)."""
+    lib = _lib.lib()
+    b, h2, w2, st = _wide_geom(buf)
+    o = w3.shape[0]
+    wv = w3.detach().float().permute(0, 3, 1, 2).reshape(o, 48, 3, 1)  # [o][s*16+c][r][0] = w3[o][c][r][s]
+    bk = _block_k(48, o, b * h2 * w2)
+    wp = pack_weight(wv, bk, buf.dtype)
+    y = _empty_cl(b, o, h2, w2, buf.dtype, buf.device)
+    d = ConvDesc()
+    d.inp, d.in_pitch = buf.data_ptr(), 16
+    d.in_x_stride, d.in_y_stride, d.in_n_stride = st["x"], st["y"], st["n"]
+    d.kw, d.pad_w = 1, 0
+    d.batch, d.in_h, d.in_w, d.in_c = b, h2, w2, 48
+    d.weight, d.bias = wp.data_ptr(), _zero_bias(o, buf.device).data_ptr()
+    d.out, d.out_pitch, d.out_c = y.data_ptr(), o, o
+    d.ksize, d.stride, d.pad = 3, 1, 1
+    d.act, d.dtype, d.block_k, d.block_n = _lib.ACT_NONE, _lib.dtype_code(buf.dtype), bk, 0
+    _lib.check(lib.y5_conv_bn_silu_fwd(C.byref(d), _st(buf.device)), "stem conv (wide pixels)")
+    return y
+
+
+def stem_wgrad_wide(buf: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """fp32 gradient of the (O,16,3,3) space-to-depth stem filter from the padded image buffer and dy (B,O,H/2,W/2)."""
+    lib = _lib.lib()
+    b, h2, w2, st = _wide_geom(buf)
+    dy, dp = _nhwc(dy)
+    o = dy.shape[1]
+    dw = torch.empty(o, 3, 1, 48, dtype=torch.float32, device=buf.device)
+    d = WgradDesc()
+    d.inp, d.in_pitch = buf.data_ptr(), 16
+    d.in_x_stride, d.in_y_stride, d.in_n_stride = st["x"], st["y"], st["n"]
+    d.kw, d.pad_w = 1, 0
+    d.batch, d.in_h, d.in_w, d.in_c = b, h2, w2, 48
+    d.dout, d.dout_pitch, d.out_c = dy.data_ptr(), dp, o
+    d.dweight = dw.data_ptr()
+    d.ksize, d.stride, d.pad = 3, 1, 1
+    d.dtype, d.accumulate = _lib.dtype_code(buf.dtype), 0
+    _lib.check(lib.y5_conv_wgrad(C.byref(d), _st(buf.device)), "stem wgrad (wide pixels)")
+    return dw.view(o, 3, 3, 16).permute(0, 3, 1, 2)  # [o][r][s][c] -> (O,16,3,3)
+
+
 _stem_idx_cache: dict = {}
 
 
@@ -250,12 +306,17 @@ class _ConvBnAct(torch.autograd.Function):
             ke, se, pe = 3, 1, 1
         else:
             w_eff, ke, se, pe = weight, k, s, p
-        x, xp = _nhwc(x)
-        bsz, _, h, w_ = x.shape
-        m_rows = bsz * ((h + 2 * pe - ke) // se + 1) * ((w_ + 2 * pe - ke) // se + 1)
-        need_dx = ctx.needs_input_grad[0] and not stem
-        wp, wp_dg, bk_f, bk_d = pack_weights(w_eff, x.dtype, m_rows, True, need_dx)
-        y = conv_packed(x, xp, wp, bk_f, None, w_eff.shape[0], ke, se, pe, act=False)
+        wide = stem == 2  # x is the (B, H/2, W/2 + 2, 16) zero-padded NHWC buffer of stem_input
+        if wide:
+            y = stem_conv_wide(x, w_eff)
+            wp_dg, bk_d = None, 0
+        else:
+            x, xp = _nhwc(x)
+            bsz, _, h, w_ = x.shape
+            m_rows = bsz * ((h + 2 * pe - ke) // se + 1) * ((w_ + 2 * pe - ke) // se + 1)
+            need_dx = ctx.needs_input_grad[0] and not stem
+            wp, wp_dg, bk_f, bk_d = pack_weights(w_eff, x.dtype, m_rows, True, need_dx)
+            y = conv_packed(x, xp, wp, bk_f, None, w_eff.shape[0], ke, se, pe, act=False)
         b, c, ho, wo = y.shape
         rows = b * ho * wo
         code = _lib.dtype_code(y.dtype)
@@ -287,6 +348,7 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.save_for_backward(x, weight, y, mean, invstd, g32, b32, wp_dg)
         ctx.cfg = (k, s, p, act, training, stem, ke, se, pe)
         ctx.bk_d = bk_d
+        ctx.wide = wide
         ctx.pdtypes = (gamma.dtype, beta.dtype)
         return z
 
@@ -310,7 +372,7 @@ class _ConvBnAct(torch.autograd.Function):
         _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), dzp, dy.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
                                      g32.data_ptr(), b32.data_ptr(), 1 if act else 0, dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
                                      _st(dev)), "bn_act_bwd")
-        dw = conv_wgrad(x, dy, ke, se, pe)
+        dw = stem_wgrad_wide(x, dy) if ctx.wide else conv_wgrad(x, dy, ke, se, pe)
         if stem:  # (O,16,3,3) gradient of the space-to-depth filter -> (O,3,6,6)
             _, inv_idx = _stem_index(dev)
             dw = dw.reshape(dw.shape[0], -1)[:, inv_idx].view(weight.shape)
@@ -375,7 +437,7 @@ def train_dtype(model) -> torch.dtype:
     return dt
 
 
-def conv_module(m, x, stem: bool = False, residual=None):
+def conv_module(m, x, stem: int = 0, residual=None):  # stem: 0 no, 1 space-to-depth 3x3x16, 2 wide-pixel 3x1x48
     bn = getattr(m, "bn", None)
     if bn is None:
         raise RuntimeError("y5b200: cannot train a fused model (Conv without BatchNorm); build it unfused")
@@ -486,6 +548,11 @@ def stem_input(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if c != 3 or h % 2 or w % 2:
         raise ValueError(f"y5b200: expected a (B,3,even,even) image batch, got {tuple(img.shape)}")
     img = img.contiguous()
+    if stem_wide_enabled():  # (B, H/2, W/2 + 2, 16) NHWC with a zero cell at both ends of every row
+        out = torch.zeros(b, h // 2, w // 2 + 2, 16, dtype=dtype, device=img.device)
+        _lib.check(lib.y5_stem_s2d(img.data_ptr(), _lib.dtype_code(img.dtype), out.data_ptr(), _lib.dtype_code(dtype), b, h, w, w // 2 + 2, 1,
+                                   _st(img.device)), "stem_s2d")
+        return out
     out = _empty_cl(b, 16, h // 2, w // 2, dtype, img.device)
     _lib.check(lib.y5_stem_s2d(img.data_ptr(), _lib.dtype_code(img.dtype), out.data_ptr(), _lib.dtype_code(dtype), b, h, w, w // 2, 0,
                                _st(img.device)), "stem_s2d")
@@ -552,7 +619,7 @@ def forward_train(model, img: torch.Tensor):
         _arena.reset(img.device)
         for i, m in enumerate(layers):
             if i == 0:
-                x = conv_module(m, stem_input(img, dt), stem=True)
+                x = conv_module(m, stem_input(img, dt), stem=2 if stem_wide_enabled() else 1)
             else:
                 if m.f != -1:
                     x = ys[m.f] if isinstance(m.f, int) else [x if j == -1 else ys[j] for j in m.f]
