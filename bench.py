@@ -441,7 +441,7 @@ def main():
     from yolov5_b200.cfg import model_cfg
     from yolov5_b200.models.yolo import DetectionModel, SegmentationModel
     from yolov5_b200.parallel import aggregate_throughput
-    from yolov5_b200.utils.general import nms_device, non_max_suppression
+    from yolov5_b200.utils.general import nms_device
 
     seg = model_name.endswith("-seg")
     nms_kw = dict(NMS_KW, nm=32) if seg else dict(NMS_KW)

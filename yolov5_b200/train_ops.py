@@ -29,8 +29,6 @@ from . import _lib
 from ._lib import ConvDesc, WgradDesc
 from .engine import pack_weight
 
-_CL = torch.channels_last
-
 
 def _st(dev):
     return C.c_void_p(_lib.stream_ptr(dev))
