@@ -88,6 +88,11 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             step()
+        # the capture baked in the address of the BN-sum arena (allocated during warm-up, outside the graph's pool): keep it
+        # alive even if a later eager forward of another shape makes the arena grow
+        from .. import train_ops
+
+        self._arena_buf = train_ops._arena.buf
         # undo what the warm-up touched: BN running statistics / batch counters, momentum buffers
         model.load_state_dict(state)
         for st in optimizer.state.values():
