@@ -287,8 +287,65 @@ def gen_train():
     np.savez_compressed(f"{HERE}/train_step.npz", **store)
 
 
+def gen_post():
+    """Post-NMS steps that SURVEY.md section 8(f) ranks next (mask post-processing, metric matching): the real reference's
+    process_mask / crop_mask / scale_boxes / process_batch on seeded inputs, asserted equal to oracle/post_ref.py."""
+    from utils.general import scale_boxes
+    from utils.metrics import process_batch
+    from utils.segment.general import process_mask
+
+    from oracle import post_ref
+
+    rs = np.random.RandomState(7)
+    store = {}
+    # process_mask: 32 prototypes at 40x56 for a 160x224 input, 9 detections
+    protos = rs.randn(32, 40, 56).astype(np.float32)
+    coef = (rs.randn(9, 32) * 0.5).astype(np.float32)
+    xy = rs.uniform(0, 1, (9, 2)) * np.array([224, 160]) * 0.6
+    wh = rs.uniform(0.1, 0.4, (9, 2)) * np.array([224, 160])
+    boxes = np.concatenate((xy, xy + wh), 1).astype(np.float32)
+    for up in (False, True):
+        ref = process_mask(torch.from_numpy(protos), torch.from_numpy(coef), torch.from_numpy(boxes), (160, 224), upsample=up).numpy()
+        got, val = post_ref.process_mask(protos, coef, boxes, (160, 224), upsample=up)
+        off = (ref != got)
+        assert ref.shape == got.shape and (not off.any() or np.abs(val[off] - 0.5).max() < 1e-5), (up, int(off.sum()))
+        store[f"mask.up{int(up)}"] = np.packbits(ref.astype(bool), axis=None)
+        store[f"mask.up{int(up)}.shape"] = np.array(ref.shape)
+    store.update({"mask.protos": protos, "mask.coef": coef, "mask.boxes": boxes, "mask.input_hw": np.array([160, 224])})
+    # scale_boxes: letterboxed 640x640 -> 480x640 original, with and without an explicit ratio_pad
+    b = (rs.uniform(-20, 660, (50, 4))).astype(np.float32)
+    for tag, rp in (("auto", None), ("given", ((0.75, 0.75), (10.0, 80.0)))):
+        ref = scale_boxes((640, 640), torch.from_numpy(b.copy()), (480, 640), rp).numpy()
+        got = post_ref.scale_boxes((640, 640), b, (480, 640), rp)
+        assert np.allclose(ref, got, rtol=0, atol=1e-4), tag
+        store[f"scale.{tag}"] = ref
+    store["scale.in"] = b
+    # process_batch: 3 cases (dense matches with shared labels, no labels, no detections)
+    iouv = np.linspace(0.5, 0.95, 10).astype(np.float32)
+    for case, (nd, nl) in enumerate(((120, 14), (30, 0), (0, 6), (200, 40))):
+        lab_xy = rs.uniform(50, 500, (nl, 2))
+        lab_wh = rs.uniform(30, 120, (nl, 2))
+        labels = np.concatenate((rs.randint(0, 3, (nl, 1)), lab_xy, lab_xy + lab_wh), 1).astype(np.float32)
+        if nl and nd:
+            src = rs.randint(0, nl, nd)
+            jit = rs.normal(0, 6, (nd, 4))
+            det_box = labels[src, 1:] + jit
+            cls = np.where(rs.uniform(size=nd) < 0.85, labels[src, 0], rs.randint(0, 3, nd))
+        else:
+            det_box = np.concatenate((rs.uniform(0, 300, (nd, 2)), rs.uniform(310, 600, (nd, 2))), 1)
+            cls = rs.randint(0, 3, nd)
+        det = np.concatenate((det_box, rs.uniform(0.1, 1, (nd, 1)), cls[:, None]), 1).astype(np.float32)
+        ref = process_batch(torch.from_numpy(det), torch.from_numpy(labels), torch.from_numpy(iouv)).numpy()
+        got = post_ref.process_batch(det, labels, iouv)
+        assert ref.shape == got.shape and np.array_equal(ref, got), (case, int((ref != got).sum()))
+        store[f"match{case}.det"], store[f"match{case}.labels"], store[f"match{case}.correct"] = det, labels, ref
+        print(f"process_batch case {case}: {nd} detections, {nl} labels, true positives per threshold {ref.sum(0).tolist()}")
+    store["match.iouv"] = iouv
+    np.savez_compressed(f"{HERE}/post.npz", **store)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg", "model", "nms", "loss", "train"]
+    which = sys.argv[1:] or ["cfg", "model", "nms", "loss", "train", "post"]
     for w in which:
-        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss, "train": gen_train}[w]()
+        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss, "train": gen_train, "post": gen_post}[w]()
     print("golden fixtures written to", HERE)

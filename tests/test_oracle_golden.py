@@ -149,3 +149,26 @@ def test_oracle_training_step_matches_reference_fixture():
             assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max(), key
         elif key.startswith("gnorm."):
             assert abs(float(params[key[6:]].grad.norm()) - float(g[key][0])) <= 1e-3 * float(g[key][0]) + 1e-9, key
+
+
+def test_post_nms_oracles_match_reference_fixture():
+    """oracle/post_ref.py (process_mask, scale_boxes, process_batch: the SURVEY 8(f) rows that come next) against
+    tests/golden/post.npz, which holds the real reference's outputs."""
+    import numpy as np
+
+    from oracle import post_ref
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "post.npz"))
+    hw = tuple(int(v) for v in g["mask.input_hw"])
+    for up in (0, 1):
+        shape = tuple(int(v) for v in g[f"mask.up{up}.shape"])
+        ref = np.unpackbits(g[f"mask.up{up}"])[: int(np.prod(shape))].reshape(shape).astype(np.float32)
+        got, val = post_ref.process_mask(g["mask.protos"], g["mask.coef"], g["mask.boxes"], hw, upsample=bool(up))
+        off = ref != got
+        assert got.shape == shape and (not off.any() or np.abs(val[off] - 0.5).max() < 1e-5), int(off.sum())
+    assert np.allclose(post_ref.scale_boxes((640, 640), g["scale.in"], (480, 640)), g["scale.auto"], rtol=0, atol=1e-4)
+    assert np.allclose(post_ref.scale_boxes((640, 640), g["scale.in"], (480, 640), ((0.75, 0.75), (10.0, 80.0))), g["scale.given"],
+                       rtol=0, atol=1e-4)
+    for case in range(4):
+        got = post_ref.process_batch(g[f"match{case}.det"], g[f"match{case}.labels"], g["match.iouv"])
+        assert np.array_equal(got, g[f"match{case}.correct"]), case
