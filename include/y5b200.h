@@ -200,6 +200,14 @@ int64_t y5_loss_workspace_bytes(const y5_loss_params* p);
  * build_targets result can be read back with y5_loss_read_targets for parity tests */
 int y5_loss_fwd_bwd(const y5_loss_params* p, const void* const* pl, const float* targets, const float* anchors,
                     float* out_loss, void* const* grad, void* workspace, int64_t workspace_bytes, void* stream);
+/* same, with the upstream gradient of the loss read from DEVICE memory: grad[l] = d(out_loss[0])/dp * p->grad_scale *
+ * (*grad_scale_dev), multiplied in fp32 BEFORE the result is rounded to the prediction dtype -- what autograd does for
+ * `scaler.scale(loss).backward()` (train.py:410): a GradScaler factor of 65536 (x WORLD_SIZE) neither overflows fp16 on
+ * the way nor flushes small objectness gradients to zero.  grad_scale_dev may be NULL (= 1).  Targets whose image index
+ * is outside [0, batch) or whose class is outside [0, nc) are ignored (the reference raises IndexError for them). */
+int y5_loss_fwd_bwd_scaled(const y5_loss_params* p, const void* const* pl, const float* targets, const float* anchors,
+                           float* out_loss, void* const* grad, const float* grad_scale_dev, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 int y5_loss_read_targets(const y5_loss_params* p, const void* workspace, int32_t level, int64_t* idx5_host,
                          float* tbox_host, int32_t* count_host, void* stream);
 
@@ -275,6 +283,105 @@ int y5_sppf_pool_bwd(const void* cat, int32_t cat_pitch, const void* dcat, int32
 /* y[n, 2i, 2j, :] = x[n, i, j, :], other pixels of the (2h, 2w) output zero */
 int y5_zero_stuff2x(const void* x, int32_t x_pitch, void* y, int32_t y_pitch, int32_t batch, int32_t h, int32_t w,
                     int32_t c, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The callers either side of the hot path, batched on the device, no host synchronisation.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Pre-processing: letterbox (utils/augmentations.py:85-115: cv2.resize INTER_LINEAR to (new_w,new_h), constant border) +
+ * BGR->RGB + HWC->CHW (utils/dataloaders.py:354-357) + uint8 -> float /255 (detect.py:205-208, val.py:259-262,
+ * models/common.py:924-926) for a batch of device-resident uint8 HWC images of different sizes.  The resize is OpenCV's
+ * fixed-point bilinear kernel restated bit for bit (oracle/pre_ref.py, pinned against the installed cv2).  The geometry
+ * (new_w/new_h/top/left) is computed by the caller exactly as the reference's letterbox() does. */
+typedef struct y5_letterbox_image {
+    const void* data;       /* uint8 HWC, 3 channels, device memory */
+    int32_t src_h, src_w;
+    int32_t row_bytes;      /* bytes between source rows (>= 3*src_w) */
+    int32_t new_h, new_w;   /* size after cv2.resize ("new_unpad") */
+    int32_t top, left;      /* border offsets inside the (out_h, out_w) canvas */
+} y5_letterbox_image;
+int y5_letterbox_max_images(void); /* descriptors are consumed in groups of this many per launch */
+/* out: out_dtype Y5_U8 -> (n,3,out_h,out_w) bytes (what the dataloader yields); Y5_F16/BF16/F32 -> the same /255;
+ * s2d != 0 (fp16/bf16 only) -> the stem's 2x2 space-to-depth cells, layout and out_row_px/out_x_off as in y5_stem_s2d.
+ * `images` is a HOST array (copied into the launch parameters). */
+int y5_letterbox(const y5_letterbox_image* images, int32_t n_images, int32_t out_h, int32_t out_w, int32_t swap_rb,
+                 int32_t pad_value, void* out, int32_t out_dtype, int32_t s2d, int32_t out_row_px, int32_t out_x_off,
+                 void* stream);
+
+/* process_mask (utils/segment/general.py:25-52, crop_mask :10-22): for detection i of image img_index[i] (NULL = image 0):
+ * sigmoid(coef_i . protos[img]) at mask resolution, zeroed outside the box scaled by (mw/in_w, mh/in_h), optionally
+ * bilinearly up-sampled (align_corners=False) to (in_h,in_w), thresholded at 0.5.
+ *   mode 0: process_mask(upsample=False) -> (n, mh, mw);  mode 1: process_mask(upsample=True) -> (n, in_h, in_w);
+ *   mode 2: process_mask_native (:55-76): no low-resolution crop, the prototype window [top, left, height, width] (`window`,
+ *           HOST array of 4 ints) is up-sampled to (in_h, in_w) and cropped to the un-scaled boxes -> (n, in_h, in_w)
+ *   protos (batch, c, mh, mw) NCHW Y5_F16|Y5_BF16|Y5_F32 (read as float, like `protos.float()`); coef rows of `coef_stride`
+ *   floats (may point at column 6 of the NMS rows); boxes rows of `box_stride` floats, xyxy in network-input pixels;
+ *   out Y5_F32 {0,1} (the reference's `masks.gt_(0.5)`) or Y5_U8.
+ * Detections of the same image must be adjacent.  workspace: y5_process_mask_workspace_bytes (modes 1, 2). */
+int64_t y5_process_mask_workspace_bytes(int32_t n, int32_t mh, int32_t mw, int32_t mode);
+int y5_process_mask(const void* protos, int32_t proto_dtype, int32_t batch, int32_t c, int32_t mh, int32_t mw, const float* coef,
+                    int32_t coef_stride, const float* boxes, int32_t box_stride, const int32_t* img_index, int32_t n,
+                    int32_t in_h, int32_t in_w, int32_t mode, const int32_t* window, void* out, int32_t out_dtype,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+/* crop_mask (utils/segment/general.py:10-22): out = masks * [box contains the pixel]; masks/out (n,h,w) fp32 */
+int y5_crop_mask(const float* masks, const float* boxes, int32_t box_stride, int32_t n, int32_t h, int32_t w, float* out,
+                 void* stream);
+
+/* scale_boxes + clip_boxes (utils/general.py:613-626), in place on rows of `row_stride` floats (xyxy first).
+ * meta: per image 5 floats [gain, pad_x, pad_y, w0, h0] (device).  Image of row i = img_index[i], or i / rows_per_image
+ * when img_index is NULL (then `count`, if given, limits each image to its first count[img] rows: the padded layout
+ * y5_nms_batched produces), or 0 when both are absent. */
+int y5_scale_boxes(float* boxes, int32_t row_stride, int64_t n_rows, const int32_t* img_index, int32_t rows_per_image,
+                   const int32_t* count, const float* meta, void* stream);
+/* val.py:303-306 for the whole batch: targets (nt,6) [img, cls, cx, cy, w, h] in network-input pixels ->
+ * out (nt,6) [img, cls, x1, y1, x2, y2] in native pixels (xywh2xyxy, then scale_boxes with the image's meta). */
+int y5_labels_native(const float* targets, int32_t nt, const float* meta, float* out, void* stream);
+/* process_batch (utils/metrics.py:224-265, box branch) for every image of a batch in one launch:
+ *   det (batch, max_det, row_stride>=6) fp32 rows [x1,y1,x2,y2,conf,cls,...] in native pixels (image b at det + b*img_stride),
+ *   count[b] valid rows (NULL = max_det); labels (nt,6) [img, cls, x1,y1,x2,y2] in any order; iouv (niou) thresholds;
+ *   correct (batch, max_det, niou) uint8: the reference's boolean matrix (rows >= count[b] are 0).  Bit-exact. */
+int y5_match_batch(const float* det, int64_t img_stride, int32_t row_stride, const int32_t* count, int32_t batch,
+                   int32_t max_det, const float* labels, int32_t nt, const float* iouv, int32_t niou, float eps,
+                   uint8_t* correct, void* stream);
+
+/* Fused optimizer step (train.py:413-421): un-scale + clip_grad_norm_ + SGD(momentum, nesterov) over parameter groups
+ * (utils/torch_utils.py:256-289) + optimizer.zero_grad + ModelEMA.update (utils/torch_utils.py:359-368) in two
+ * multi-tensor launches.  All tensors fp32.  `table`, `chunk_*`, `hyper`, `partial` are DEVICE arrays owned by the caller:
+ *   table[t]            one entry per tensor (buffers take part in the EMA only: grad = mom = NULL)
+ *   chunk_tensor/index  block c handles elements [chunk_index[c]*y5_opt_chunk_elems(), +y5_opt_chunk_elems()) of tensor chunk_tensor[c]
+ *   hyper               floats: [Y5_OPT_INV_SCALE] 1/loss scale, [Y5_OPT_MAX_NORM] clip norm (<= 0: off), [Y5_OPT_EMA_DECAY],
+ *                       [Y5_OPT_EMA_TAU], [Y5_OPT_EMA_UPDATES] counter (advanced by the call when do_ema),
+ *                       [Y5_OPT_OUT_NORM] total gradient norm (written), [Y5_OPT_OUT_SKIPPED] 1 if a non-finite gradient
+ *                       made the step skip (written), then per group g at Y5_OPT_GROUPS + 4g: lr, momentum, weight_decay, nesterov
+ *   partial             2 * n_chunks floats of scratch */
+typedef struct y5_opt_tensor {
+    void* param;
+    void* grad;
+    void* mom;
+    void* ema;
+    int64_t numel;
+    int32_t group;
+    int32_t reserved;
+} y5_opt_tensor;
+#define Y5_OPT_INV_SCALE 0
+#define Y5_OPT_MAX_NORM 1
+#define Y5_OPT_EMA_DECAY 2
+#define Y5_OPT_EMA_TAU 3
+#define Y5_OPT_EMA_UPDATES 4
+#define Y5_OPT_OUT_NORM 5
+#define Y5_OPT_OUT_SKIPPED 6
+#define Y5_OPT_GROUPS 8
+int32_t y5_opt_chunk_elems(void);
+int y5_opt_step(const y5_opt_tensor* table, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                float* hyper, float* partial, int32_t do_step, int32_t do_ema, int32_t zero_grad, void* stream);
+
+/* Fold eval-mode BatchNorm into a conv and pack it for y5_conv_bn_silu_fwd in ONE launch (utils/torch_utils.py:224-254):
+ *   packed[o][r][s][i_pad] = w[o][i][r][s] * gamma[o] / sqrt(var[o] + eps)   (activation dtype, zero padded)
+ *   bias_out[o]            = beta[o] + (conv_bias[o] - mean[o]) * gamma[o] / sqrt(var[o] + eps)   (fp32)
+ * gamma == NULL: no BatchNorm (already fused conv): packed = w, bias_out = conv_bias (or 0).  w: OIHW Y5_F32|F16|BF16;
+ * BN tensors fp32 or the weight dtype (`bn_dtype`).  out_c_pad >= out_c rows are written (extra rows zero, bias 0). */
+int y5_fold_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t kh, int32_t kw, const void* conv_bias,
+                 const void* gamma, const void* beta, const void* mean, const void* var, int32_t bn_dtype, float eps,
+                 void* packed, int32_t in_c_pad, int32_t out_c_pad, float* bias_out, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -135,3 +135,58 @@ def synth_targets(bs: int, seed: int = 1, nc: int = 80) -> np.ndarray:
         wh = np.exp(rs.uniform(-4, -1, (n, 2)))
         rows.append(np.concatenate((np.full((n, 1), b), cls[:, None], xy, wh), 1))
     return np.concatenate(rows, 0).astype(np.float32)
+
+
+def compute_loss_torch(p, targets, anchors, hyp, balance=(4.0, 1.0, 0.4)):
+    """The same loss as `compute_loss`, expressed with torch ops ON THE DEVICE OF `p` the way the reference executes it
+    (utils/loss.py:134-247: build_targets with boolean-mask indexing, gather / scatter, BCEWithLogits): the loss half of the
+    "reference's own torch-cuda build" arm in bench.py.  Checked against `compute_loss` by tests/test_oracle_golden.py."""
+    dev = p[0].device
+    targets = targets.to(dev, torch.float32).view(-1, 6)
+    anchors = anchors.to(dev, torch.float32)
+    na, nt, nc = anchors.shape[1], targets.shape[0], p[0].shape[-1] - 5
+    cp, cn = 1.0 - 0.5 * hyp.get("label_smoothing", 0.0), 0.5 * hyp.get("label_smoothing", 0.0)
+    pw_cls = torch.tensor([hyp["cls_pw"]], device=dev)
+    pw_obj = torch.tensor([hyp["obj_pw"]], device=dev)
+    ai = torch.arange(na, device=dev).float().view(na, 1).repeat(1, nt)
+    t7 = torch.cat((targets.repeat(na, 1, 1), ai[..., None]), 2)
+    off = torch.from_numpy(_OFF).to(dev)
+    gain = torch.ones(7, device=dev)
+    lcls, lbox, lobj = (torch.zeros(1, device=dev) for _ in range(3))
+    for i, pi in enumerate(p):
+        ny, nx = pi.shape[2:4]
+        gain[2:6] = torch.tensor([nx, ny, nx, ny], device=dev, dtype=torch.float32)
+        t = t7 * gain
+        if nt:
+            r = t[..., 4:6] / anchors[i][:, None]
+            t = t[torch.max(r, 1 / r).max(2)[0] < hyp["anchor_t"]]
+            gxy = t[:, 2:4]
+            gxi = gain[[2, 3]] - gxy
+            j, k = ((gxy % 1 < 0.5) & (gxy > 1)).T
+            l, m = ((gxi % 1 < 0.5) & (gxi > 1)).T
+            sel = torch.stack((torch.ones_like(j), j, k, l, m))
+            t = t.repeat((5, 1, 1))[sel]
+            offsets = (torch.zeros_like(gxy)[None] + off[:, None])[sel]
+        else:
+            t, offsets = t7[0], 0
+        b, c = t[:, 0].long(), t[:, 1].long()
+        gxy, gwh, a = t[:, 2:4], t[:, 4:6], t[:, 6].long()
+        gij = (gxy - offsets).long()
+        gi, gj = gij[:, 0].clamp(0, nx - 1), gij[:, 1].clamp(0, ny - 1)
+        tbox = torch.cat((gxy - torch.stack((gi, gj), 1), gwh), 1)
+        tobj = torch.zeros(pi.shape[:4], dtype=pi.dtype, device=dev)
+        n = b.shape[0]
+        if n:
+            ps = pi[b, a, gj, gi]
+            pxy = ps[:, 0:2].sigmoid() * 2 - 0.5
+            pwh = (ps[:, 2:4].sigmoid() * 2) ** 2 * anchors[i][a]
+            iou = bbox_ciou(torch.cat((pxy, pwh), 1), tbox)
+            lbox = lbox + (1.0 - iou).mean()
+            tobj[b, a, gj, gi] = iou.detach().clamp(0).type(tobj.dtype)
+            if nc > 1:
+                tc = torch.full_like(ps[:, 5:], cn)
+                tc[torch.arange(n, device=dev), c] = cp
+                lcls = lcls + F.binary_cross_entropy_with_logits(ps[:, 5:], tc, pos_weight=pw_cls)
+        lobj = lobj + F.binary_cross_entropy_with_logits(pi[..., 4], tobj, pos_weight=pw_obj) * balance[i]
+    lbox, lobj, lcls = lbox * hyp["box"], lobj * hyp["obj"], lcls * hyp["cls"]
+    return (lbox + lobj + lcls) * p[0].shape[0], torch.cat((lbox, lobj, lcls)).detach()

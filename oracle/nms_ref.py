@@ -94,8 +94,13 @@ def non_max_suppression(
     nm: int = 0,
     dtype: str = "fp32",
     return_index: bool = False,
+    labels=(),
 ):
     """prediction: (B, N, 5+nc+nm) fp32 array holding values exactly representable in ``dtype``.
+
+    ``labels`` (autolabelling, reference :706-712): per image an (m,5) array [cls, x, y, w, h]; its rows are appended to the
+    image's candidates with obj = class score = 1.  The reference's ``torch.cat((x, v), 0)`` with an fp32 ``v`` promotes that
+    image's rows to fp32, so everything after the first objectness test (:686) runs in fp32 for such an image.
 
     Returns a list of B fp32 arrays (n_i, 6+nm) = [x1,y1,x2,y2,conf,cls,(masks)]; with ``return_index`` also the
     list of int64 arrays of candidate ids ``row*nc + cls`` of the kept detections (the integer result).
@@ -113,20 +118,32 @@ def non_max_suppression(
         x = pred[xi]
         rows = np.nonzero(x[:, 4] > thr)[0]  # :686, :703
         empty = (np.zeros((0, 6 + nm), np.float32), np.zeros((0,), np.int64))
-        if rows.size == 0:
-            outs.append(empty[0]); idxs.append(empty[1]); continue
         x = x[rows]
-        scaled = round_to(x[:, 5:] * x[:, 4:5], dtype)  # :719  (cls AND mask columns are scaled by obj)
-        half = round_to(x[:, 2:4] / np.float32(2), dtype)  # xywh2xyxy in the input dtype
-        box = np.concatenate((round_to(x[:, 0:2] - half, dtype), round_to(x[:, 0:2] + half, dtype)), 1)
+        idt, ithr = dtype, thr  # dtype / threshold of this image from here on
+        if labels and xi < len(labels) and len(labels[xi]):  # :706-712
+            lb = np.asarray(labels[xi], np.float32)
+            v = np.zeros((len(lb), no), np.float32)
+            v[:, :4] = lb[:, 1:5]
+            v[:, 4] = 1.0
+            v[np.arange(len(lb)), lb[:, 0].astype(np.int64) + 5] = 1.0
+            x = np.concatenate((x, v), 0)
+            rows = np.concatenate((rows, pred.shape[1] + np.arange(len(lb))))  # appended rows get ids past the last prediction row
+            idt, ithr = "fp32", np.float32(conf_thres)
+        if x.shape[0] == 0:
+            outs.append(empty[0]); idxs.append(empty[1]); continue
+        dtype_i = idt
+        scaled = round_to(x[:, 5:] * x[:, 4:5], dtype_i)  # :719  (cls AND mask columns are scaled by obj)
+        half = round_to(x[:, 2:4] / np.float32(2), dtype_i)  # xywh2xyxy in the input dtype
+        box = np.concatenate((round_to(x[:, 0:2] - half, dtype_i), round_to(x[:, 0:2] + half, dtype_i)), 1)
         cls_conf, mask = scaled[:, :nc], scaled[:, nc:]
+        thr_i = ithr
         if multi_label:
-            i, j = np.nonzero(cls_conf > thr)  # row-major (i, j) order, like Tensor.nonzero  :727
+            i, j = np.nonzero(cls_conf > thr_i)  # row-major (i, j) order, like Tensor.nonzero  :727
             conf = cls_conf[i, j]
         else:
             j = cls_conf.argmax(1)  # first maximum
             conf = cls_conf[np.arange(len(j)), j]
-            i = np.nonzero(conf > thr)[0]  # :731
+            i = np.nonzero(conf > thr_i)[0]  # :731
             j, conf = j[i], conf[i]
         cand = rows[i].astype(np.int64) * nc + j.astype(np.int64)
         det = np.concatenate((box[i], conf[:, None], j[:, None].astype(np.float32), mask[i]), 1).astype(np.float32)

@@ -11,6 +11,7 @@ the absent `ultralytics` package in the reference: pinned only to the shim's res
 Reference lines restated (paths relative to /root/reference):
   utils/segment/general.py:10-22   crop_mask                      -> crop_mask
   utils/segment/general.py:25-52   process_mask                   -> process_mask
+  utils/segment/general.py:55-76   process_mask_native            -> process_mask_native
   utils/general.py:613-626         scale_boxes (+ clip_boxes)     -> scale_boxes
   utils/metrics.py:224-265         process_batch (box branch)     -> process_batch
 """
@@ -69,6 +70,20 @@ def process_mask(protos: np.ndarray, masks_in: np.ndarray, bboxes: np.ndarray, s
     m = crop_mask(m, b)
     if upsample:
         m = bilinear_resize(m, (ih, iw))
+    return (m > np.float32(0.5)).astype(np.float32), m
+
+
+def process_mask_native(protos: np.ndarray, masks_in: np.ndarray, bboxes: np.ndarray, shape):
+    """Up-sample the un-padded window of the prototype-resolution masks to `shape`, THEN crop with the (un-scaled) boxes."""
+    c, mh, mw = protos.shape
+    logits = masks_in.astype(np.float32) @ protos.astype(np.float32).reshape(c, -1)
+    m = (np.float32(1) / (np.float32(1) + np.exp(-logits, dtype=np.float32))).reshape(-1, mh, mw)
+    gain = min(mh / shape[0], mw / shape[1])
+    pad = (mw - shape[1] * gain) / 2, (mh - shape[0] * gain) / 2
+    top, left = int(pad[1]), int(pad[0])
+    bottom, right = int(mh - pad[1]), int(mw - pad[0])
+    m = bilinear_resize(m[:, top:bottom, left:right], shape)
+    m = crop_mask(m, bboxes.astype(np.float32))
     return (m > np.float32(0.5)).astype(np.float32), m
 
 

@@ -195,6 +195,30 @@ def gen_nms():
         c["pinned"] = how
         meta.append({k: v for k, v in c.items()})
         print(f"NMS {c['tag']}: oracle == reference {how}; dets/img {[r.shape[0] for r in ref]}")
+    # (3) apriori labels (val.py --save-hybrid, utils/general.py:706-712): the reference vs the oracle
+    from utils.general import non_max_suppression as ref_nms
+
+    for tag, dt in (("hybrid_fp16", "fp16"), ("hybrid_fp32", "fp32")):
+        pred = nms_ref.synth_predictions(3, 6300, 80, 0, 11, dt)
+        lrs = np.random.RandomState(12)
+        labels = []
+        for b in range(3):
+            m = [4, 0, 7][b]
+            cxy = lrs.uniform(60, 580, (m, 2))
+            wh = lrs.uniform(20, 200, (m, 2))
+            labels.append(np.concatenate((lrs.randint(0, 80, (m, 1)), cxy, wh), 1).astype(np.float32))
+        kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=True, max_det=300)
+        tdt = {"fp32": torch.float32, "fp16": torch.float16}[dt]
+        ref = []
+        for b in range(3):  # one image per call (wall-clock abort), labels list aligned with the single image
+            ref.append(ref_nms(torch.from_numpy(pred[b : b + 1]).to(tdt), labels=[torch.from_numpy(labels[b])], **kw)[0].numpy())
+        orc = nms_ref.non_max_suppression(pred, dtype=dt, labels=labels, **kw)
+        for b, (r, o) in enumerate(zip(ref, orc)):
+            assert r.shape == o.shape and np.array_equal(canon_ties(r), canon_ties(o)), (tag, b, r.shape, o.shape)
+            store[f"{tag}.{b}"] = o
+            store[f"{tag}.labels{b}"] = labels[b]
+        meta.append(dict(tag=tag, bs=3, n=6300, nc=80, nm=0, seed=11, dtype=dt, kw=kw, labels=True, pinned="exact up to the order inside equal-score runs"))
+        print(f"NMS {tag}: oracle == reference with apriori labels; dets/img {[r.shape[0] for r in ref]}")
     store["meta"] = np.array(json.dumps(meta))
     np.savez_compressed(f"{HERE}/nms.npz", **store)
 
@@ -311,6 +335,21 @@ def gen_post():
         assert ref.shape == got.shape and (not off.any() or np.abs(val[off] - 0.5).max() < 1e-5), (up, int(off.sum()))
         store[f"mask.up{int(up)}"] = np.packbits(ref.astype(bool), axis=None)
         store[f"mask.up{int(up)}.shape"] = np.array(ref.shape)
+    from utils.segment.general import process_mask_native
+
+    ref = process_mask_native(torch.from_numpy(protos), torch.from_numpy(coef), torch.from_numpy(boxes), (160, 224)).numpy()
+    got, val = post_ref.process_mask_native(protos, coef, boxes, (160, 224))
+    off = ref != got
+    assert ref.shape == got.shape and (not off.any() or np.abs(val[off] - 0.5).max() < 1e-5), int(off.sum())
+    store["mask.native"] = np.packbits(ref.astype(bool), axis=None)
+    store["mask.native.shape"] = np.array(ref.shape)
+    # a letterboxed (padded) prototype map: 40x56 prototypes for a 128x224 input -> the un-padded window is rows 4..36
+    ref = process_mask_native(torch.from_numpy(protos), torch.from_numpy(coef), torch.from_numpy(boxes), (128, 224)).numpy()
+    got, val = post_ref.process_mask_native(protos, coef, boxes, (128, 224))
+    off = ref != got
+    assert ref.shape == got.shape and (not off.any() or np.abs(val[off] - 0.5).max() < 1e-5), int(off.sum())
+    store["mask.native_pad"] = np.packbits(ref.astype(bool), axis=None)
+    store["mask.native_pad.shape"] = np.array(ref.shape)
     store.update({"mask.protos": protos, "mask.coef": coef, "mask.boxes": boxes, "mask.input_hw": np.array([160, 224])})
     # scale_boxes: letterboxed 640x640 -> 480x640 original, with and without an explicit ratio_pad
     b = (rs.uniform(-20, 660, (50, 4))).astype(np.float32)
@@ -344,8 +383,143 @@ def gen_post():
     np.savez_compressed(f"{HERE}/post.npz", **store)
 
 
+from make_golden_cases import PRE_CASES  # noqa: E402
+
+
+def gen_pre():
+    """Step before the hot path: the reference's letterbox (cv2.resize INTER_LINEAR + copyMakeBorder) and the dataloader's
+    HWC BGR -> CHW RGB on seeded images, asserted equal -- byte for byte -- to oracle/pre_ref.py."""
+    import cv2
+    from utils.augmentations import letterbox
+
+    from oracle import pre_ref
+
+    rs = np.random.RandomState(0)
+    for t in range(200):  # the fixed-point bilinear restatement vs the installed OpenCV on random shapes
+        h, w, dh, dw = rs.randint(5, 500), rs.randint(5, 700), rs.randint(4, 500), rs.randint(4, 700)
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), pre_ref.resize_linear_u8(img, (dw, dh))), (t, h, w, dh, dw)
+    store = {}
+    for i, (h, w, seed, kw) in enumerate(PRE_CASES):
+        im = pre_ref.synth_image(h, w, seed)
+        ref, r_ratio, r_pad = letterbox(im, **kw)
+        got, g_ratio, g_pad = pre_ref.letterbox(im, **kw)
+        assert np.array_equal(ref, got) and tuple(r_ratio) == tuple(g_ratio) and tuple(r_pad) == tuple(g_pad), i
+        chw = np.ascontiguousarray(ref.transpose((2, 0, 1))[::-1])  # utils/dataloaders.py:356
+        assert np.array_equal(chw, pre_ref.to_chw_rgb(got))
+        store[f"lb{i}"] = chw
+        store[f"lb{i}.ratio_pad"] = np.array([*r_ratio, *r_pad], np.float64)
+    np.savez_compressed(f"{HERE}/pre.npz", **store)
+    print(f"letterbox: oracle == reference (cv2 {cv2.__version__}) byte for byte on {len(PRE_CASES)} cases + 200 random resizes")
+
+
+def gen_optim():
+    """Step after backward (train.py:413-421): torch.optim.SGD(nesterov) over the reference's 3-group layout + clip_grad_norm_
+    + the reference's ModelEMA, vs oracle/optim_ref.py."""
+    from utils.torch_utils import ModelEMA
+
+    from oracle import optim_ref
+
+    store = {}
+    hyper = [dict(lr=0.01, momentum=0.937, weight_decay=0.0, nesterov=True), dict(lr=0.01, momentum=0.937, weight_decay=5e-4, nesterov=True),
+             dict(lr=0.1, momentum=0.8, weight_decay=0.0, nesterov=True)]
+    for case, (inv_scale, max_norm, poison) in enumerate(((1.0, 10.0, False), (1.0 / 1024, 10.0, False), (1.0, 1e9, False), (1.0 / 8, 10.0, True))):
+        params, grads, moms, emas, groups = optim_ref.synth_problem(40 + case)
+        if poison:
+            grads[3].flat[5] = np.inf
+        tp = [torch.nn.Parameter(torch.from_numpy(p.copy())) for p in params]
+
+        class Holder(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.ps = torch.nn.ParameterList(tp)
+                self.register_buffer("stat", torch.from_numpy(np.linspace(0, 1, 33, dtype=np.float32)))
+
+        model = Holder()
+        opt = torch.optim.SGD([dict(params=[tp[i] for i in range(len(tp)) if groups[i] == g], **{k: v for k, v in hyper[g].items()}) for g in range(3)],
+                              lr=0.01)
+        for i, p in enumerate(tp):  # momentum buffers as if a few steps had run
+            opt.state[p]["momentum_buffer"] = torch.from_numpy(moms[i].copy())
+            p.grad = torch.from_numpy(grads[i].copy())
+        ema = ModelEMA(model, decay=0.9999, tau=2000, updates=37)
+        with torch.no_grad():
+            for e, v in zip(ema.ema.ps, emas):
+                e.copy_(torch.from_numpy(v))
+            ema.ema.stat.copy_(torch.from_numpy(np.linspace(1, 2, 33, dtype=np.float32)))
+        # train.py:413-421
+        for p in tp:
+            p.grad.mul_(inv_scale)                                   # scaler.unscale_
+        found_inf = not all(bool(torch.isfinite(p.grad).all()) for p in tp)
+        norm = torch.nn.utils.clip_grad_norm_(tp, max_norm=max_norm)
+        if not found_inf:                                            # scaler.step skips on overflow
+            opt.step()
+        ema.update(model)
+        p_o, m_o, e_o, eb_o, gn, skipped = optim_ref.sgd_ema_step(params, grads, moms, emas, groups, hyper, inv_scale, max_norm, 0.9999, 2000.0, 37,
+                                                                 buffers=[np.linspace(0, 1, 33, dtype=np.float32)],
+                                                                 ema_buffers=[np.linspace(1, 2, 33, dtype=np.float32)])
+        assert skipped == found_inf
+        if not found_inf:
+            assert abs(gn - float(norm)) <= 1e-5 * float(norm), (gn, float(norm))
+        for i in range(len(tp)):
+            assert np.allclose(tp[i].detach().numpy(), p_o[i], rtol=2e-6, atol=1e-7), (case, i)
+            assert np.allclose(opt.state[tp[i]]["momentum_buffer"].numpy(), m_o[i], rtol=2e-6, atol=1e-7), (case, i)
+            assert np.allclose(ema.ema.ps[i].detach().numpy(), e_o[i], rtol=2e-6, atol=1e-7), (case, i)
+            sub = lambda a: a.reshape(-1)[:: optim_ref.FIXTURE_STRIDE].copy()  # noqa: E731
+            store[f"c{case}.p{i}"], store[f"c{case}.m{i}"], store[f"c{case}.e{i}"] = (sub(tp[i].detach().numpy()), sub(opt.state[tp[i]]["momentum_buffer"].numpy()),
+                                                                                      sub(ema.ema.ps[i].detach().numpy()))
+        assert np.allclose(ema.ema.stat.numpy(), eb_o[0], rtol=2e-6, atol=1e-7)
+        store[f"c{case}.ebuf"] = ema.ema.stat.numpy()
+        store[f"c{case}.cfg"] = np.array([inv_scale, max_norm, float(poison), float(norm) if not found_inf else -1.0])
+    store["hyper"] = np.array(json.dumps(hyper))
+    np.savez_compressed(f"{HERE}/optim.npz", **store)
+    print("optimizer step: oracle == torch.optim.SGD + clip_grad_norm_ + reference ModelEMA on 4 cases (one with an overflow skip)")
+
+
+def tiny_cfg():
+    """yolov5 v6 topology with narrow layers (the reference's YAML grammar): small enough to commit a pickled checkpoint."""
+    cfg = json.loads(json.dumps(model_cfg("yolov5s")))
+    cm = {64: 16, 128: 16, 256: 32, 512: 64, 1024: 64}
+    for part in ("backbone", "head"):
+        for row in cfg[part]:
+            if row[2] in ("Conv", "C3", "SPPF") and isinstance(row[3][0], int):
+                row[3][0] = cm[row[3][0]]
+    cfg.update(nc=3, depth_multiple=0.33, width_multiple=1.0)
+    return cfg
+
+
+def gen_ckpt():
+    """A checkpoint pickled BY THE REFERENCE (whole-module pickle naming models.yolo.DetectionModel, models.common.Conv ...,
+    as train.py:469-482 writes them) + its forward on a seeded image: what yolov5_b200.compat / attempt_load must load."""
+    from models.yolo import DetectionModel
+
+    cfg = tiny_cfg()
+    torch.manual_seed(3)
+    m = DetectionModel(cfg, ch=3)
+    g = torch.Generator().manual_seed(4)
+    for mod in m.modules():  # non-trivial BatchNorm statistics so the fold matters
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data = torch.rand(mod.weight.shape, generator=g) + 0.5
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.1
+            mod.running_mean = torch.randn(mod.running_mean.shape, generator=g) * 0.1
+            mod.running_var = torch.rand(mod.running_var.shape, generator=g) + 0.5
+    m.names = {0: "a", 1: "b", 2: "c"}
+    m.eval()
+    x = synth_image((1, 3, 64, 96), 5)
+    with torch.no_grad():
+        z = m(x)[0].numpy()
+    from copy import deepcopy
+
+    torch.save({"epoch": -1, "best_fitness": None, "model": deepcopy(m).half(), "ema": None, "updates": 0, "optimizer": None, "opt": {},
+                "date": "fixture"}, f"{HERE}/ref_tiny.pt")
+    np.savez_compressed(f"{HERE}/ref_tiny_forward.npz", z=z, keys=np.array(json.dumps(list(m.state_dict().keys()))),
+                        cfg=np.array(json.dumps(cfg)))
+    print(f"reference-pickled checkpoint: {sum(p.numel() for p in m.parameters())} parameters, "
+          f"{os.path.getsize(f'{HERE}/ref_tiny.pt') / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg", "model", "nms", "loss", "train", "post"]
+    which = sys.argv[1:] or ["cfg", "model", "nms", "loss", "train", "post", "pre", "optim", "ckpt"]
     for w in which:
-        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss, "train": gen_train, "post": gen_post}[w]()
+        {"cfg": gen_cfg, "model": gen_model, "nms": gen_nms, "loss": gen_loss, "train": gen_train, "post": gen_post, "pre": gen_pre,
+         "optim": gen_optim, "ckpt": gen_ckpt}[w]()
     print("golden fixtures written to", HERE)

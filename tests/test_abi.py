@@ -53,6 +53,26 @@ def test_wgrad_and_bn_argument_validation_without_gpu(built_lib):
     assert lib.y5_weight_pack(None, _lib.Y5_F32, 8, 8, 1, None, 8, None, 8, _lib.Y5_F16, None) == -1
 
 
+def test_pre_post_optimizer_argument_validation_without_gpu(built_lib):
+    """The section-8(f) entry points reject bad arguments before touching the device."""
+    lib = built_lib
+    assert lib.y5_letterbox(None, 1, 640, 640, 1, 114, None, _lib.Y5_U8, 0, 0, 0, None) == -1
+    im = _lib.LetterboxImage()
+    im.data, im.src_h, im.src_w, im.row_bytes, im.new_h, im.new_w, im.top, im.left = 4096, 480, 640, 1920, 480, 640, 100, 0
+    assert lib.y5_letterbox(ctypes.byref(im), 1, 512, 640, 1, 114, 4096, _lib.Y5_U8, 0, 0, 0, None) == -1  # 100 + 480 > 512
+    assert b"does not fit" in lib.y5_last_error()
+    assert lib.y5_letterbox_max_images() >= 8
+    assert lib.y5_process_mask_workspace_bytes(10, 160, 160, 0) == 0
+    assert lib.y5_process_mask_workspace_bytes(10, 160, 160, 1) >= 10 * 160 * 160 * 4
+    assert lib.y5_process_mask(4096, _lib.Y5_F16, 1, 128, 160, 160, 4096, 38, 4096, 38, None, 3, 640, 640, 0, None, 4096, _lib.Y5_F32, None,
+                               0, None) == -2  # 128 prototype channels
+    assert lib.y5_match_batch(4096, 1800, 6, None, 2, 5000, None, 0, 4096, 10, 1e-7, 4096, None) == -2  # max_det cap
+    assert lib.y5_scale_boxes(None, 6, 10, None, 0, None, None, None) == -1
+    assert lib.y5_opt_chunk_elems() > 0 and lib.y5_opt_step(None, None, None, 4, None, None, 1, 1, 1, None) == -1
+    assert lib.y5_fold_pack(None, _lib.Y5_F32, 8, 8, 1, 1, None, None, None, None, None, _lib.Y5_F32, 1e-3, None, 8, 8, None, _lib.Y5_F16, None) == -1
+    assert lib.y5_loss_fwd_bwd_scaled(None, None, None, None, None, None, None, None, 0, None) == -1
+
+
 def test_argument_validation_without_gpu(built_lib):
     lib = built_lib
     assert lib.y5_version() == 1
@@ -91,7 +111,8 @@ def _header_structs():
 def test_ctypes_structs_match_the_c_layout(tmp_path):
     """sizeof / offsetof of every struct in the header (compiled by gcc) == the ctypes mirrors in yolov5_b200/_lib.py."""
     mirrors = {"y5_conv_desc": _lib.ConvDesc, "y5_detect_desc": _lib.DetectDesc, "y5_nms_params": _lib.NmsParams,
-               "y5_loss_params": _lib.LossParams, "y5_wgrad_desc": _lib.WgradDesc}
+               "y5_loss_params": _lib.LossParams, "y5_wgrad_desc": _lib.WgradDesc, "y5_letterbox_image": _lib.LetterboxImage,
+               "y5_opt_tensor": _lib.OptTensor}
     structs = _header_structs()
     assert sorted(structs) == sorted(mirrors), (sorted(structs), sorted(mirrors))
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]

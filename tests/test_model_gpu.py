@@ -155,3 +155,110 @@ def test_fused_checkpoint_equals_unfused(cuda):
     za = a.to(cuda).half().eval()(x)[0].float()
     zb = b.to(cuda).half().eval()(x)[0].float()
     assert float((za - zb).abs().max()) <= 2e-3 * float(za.abs().max())
+
+
+def _check_model_batch_subset(name, batch, size, dtype, dev, seed_w, seed_x, check=(0, -1), head_bias="init"):
+    """Engine on the WHOLE bench batch (tile choices depend on B*H*W); oracle and torch low-precision reference on the images
+    `check` only (images are independent in eval mode), same criterion as _check_model."""
+    cfg = model_cfg(name)
+    sd = model_ref.synth_state_dict(cfg, seed=seed_w, head_bias=head_bias)
+    x = torch.from_numpy(np.random.RandomState(seed_x).uniform(0, 1, (batch, 3, size, size)).astype(np.float32))
+    seg = name.endswith("-seg")
+    m = (SegmentationModel if seg else DetectionModel)(name)
+    m.load_state_dict(sd)
+    m = m.to(dev, dtype).eval()
+    out = m(x.to(dev, dtype))
+    sel = [i % batch for i in check]
+    xs = x[sel]
+    with torch.no_grad():
+        ref = model_ref.forward(cfg, sd, xs.to(dtype).float(), fused=True)
+    low = _torch_lowp_reference(cfg, sd, xs, dtype, dev)
+    pairs = [("z", out[0][sel], ref[0], low[0])]
+    raws, rraws, lraws = (out[2], ref[2], low[2]) if seg else (out[1], ref[1], low[1])
+    pairs += [(f"raw{l}", a[sel], b, c) for l, (a, b, c) in enumerate(zip(raws, rraws, lraws))]
+    if seg:
+        pairs.append(("proto", out[1][sel], ref[1], low[1]))
+    report = {}
+    for tag, got, r, lo in pairs:
+        got, lo = got.float().cpu(), lo.float().cpu()
+        assert got.shape == r.shape, (tag, got.shape, r.shape)
+        scale = float(r.abs().max())
+        e_eng, e_low = float((got - r).abs().max()), float((lo - r).abs().max())
+        report[tag] = (e_eng / scale, e_low / scale)
+        assert e_eng <= 1e-3 * scale + 1.5 * e_low, (name, tag, e_eng / scale, e_low / scale)
+    print("bench-shape parity", name, batch, size, dtype, {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in report.items()})
+    return m, out
+
+
+def test_bench_shape_config3_yolov5l_bs64_bf16(cuda):
+    """BASELINE config 3 (the headline): yolov5l, 64 x 3 x 640 x 640, bf16 -- the exact shapes the benchmark times."""
+    _check_model_batch_subset("yolov5l", 64, 640, torch.bfloat16, cuda, 31, 131)
+
+
+def test_bench_shape_config2_yolov5s_bs32_fp16(cuda):
+    """BASELINE config 2: yolov5s, 32 x 3 x 640 x 640, fp16, then NMS bit-exact vs the oracle on the engine's own predictions."""
+    from oracle import nms_ref
+    from yolov5_b200.utils.general import non_max_suppression
+
+    m, out = _check_model_batch_subset("yolov5s", 32, 640, torch.float16, cuda, 32, 132, head_bias="hot")
+    z = out[0]
+    dets, idx = non_max_suppression(z, 0.25, 0.45, max_det=300, return_indices=True)
+    for b in (0, 13, 31):
+        ref, ridx = nms_ref.non_max_suppression(z[b : b + 1].float().cpu().numpy(), 0.25, 0.45, max_det=300, dtype="fp16", return_index=True)
+        assert np.array_equal(idx[b].cpu().numpy(), ridx[0]) and np.array_equal(dets[b].cpu().numpy(), ref[0]), b
+
+
+def test_bench_shape_config5_yolov5x_seg_1280(cuda):
+    """BASELINE config 5 per-GPU shard: yolov5x-seg, 2 x 3 x 1280 x 1280, fp16 (Proto at 320x320, z (2, 100800, 117));
+    one image checked against the fp32 oracle."""
+    _check_model_batch_subset("yolov5x-seg", 2, 1280, torch.float16, cuda, 33, 133, check=(1,))
+
+
+def test_reference_pickled_checkpoint_runs_on_the_engine(cuda):
+    """tests/golden/ref_tiny.pt was pickled by the unmodified reference; attempt_load (compat aliases) + the val.py call
+    expressions `model(im, augment=augment)` (val.py:267) and `non_max_suppression(preds, conf, iou, labels=lb,
+    multi_label=True, agnostic=single_cls, max_det=max_det)` (val.py:277-279) against the reference's stored forward."""
+    from yolov5_b200 import compat
+    from yolov5_b200.models.experimental import attempt_load
+    from yolov5_b200.utils.general import non_max_suppression
+
+    ref = np.load(os.path.join(G, "ref_tiny_forward.npz"))
+    try:
+        model = attempt_load(os.path.join(G, "ref_tiny.pt"), device=cuda)
+    finally:
+        compat.uninstall()
+    model = model.half()
+    im = _image((1, 3, 64, 96), 5).to(cuda).half()
+    augment, compute_loss, single_cls, lb, conf_thres, iou_thres, max_det = False, None, False, [], 0.001, 0.6, 300
+    preds, train_out = model(im) if compute_loss else (model(im, augment=augment), None)   # val.py:267 verbatim
+    z = preds[0]
+    rz = ref["z"]
+    assert tuple(z.shape) == rz.shape
+    assert float(np.abs(z.float().cpu().numpy() - rz).max()) <= 2e-2 * float(np.abs(rz).max())  # checkpoint stored in fp16, engine fp16
+    out = non_max_suppression(preds, conf_thres, iou_thres, labels=lb, multi_label=True, agnostic=single_cls, max_det=max_det)  # val.py:277
+    assert len(out) == 1 and out[0].shape[1] == 6
+    # test-time augmentation (models/yolo.py:269-283): 3 scales + flip, tails clipped
+    ya, none = model(im, augment=True)
+    assert none is None and ya.shape[0] == 1 and ya.shape[2] == z.shape[2]
+    n_full = z.shape[1]
+    assert n_full < ya.shape[1] < 3 * n_full
+    # the un-flipped full-scale copy leads the TTA output (minus its largest-stride tail): same numbers as the plain forward
+    keep = n_full - n_full // 21
+    assert torch.allclose(ya[0, :keep].float(), z[0, :keep].float(), rtol=1e-3, atol=1e-3)
+
+
+def test_program_build_launches_are_library_kernels(cuda):
+    """Building a Program folds BatchNorm and packs weights through y5_fold_pack (one launch per GEMM operand), not through
+    ATen arithmetic: the library's launch counter accounts for (almost) every kernel of the first forward."""
+    from yolov5_b200 import _lib
+
+    m = DetectionModel("yolov5s")
+    m.load_state_dict(model_ref.synth_state_dict(model_cfg("yolov5s"), seed=9))
+    m = m.half().to(cuda).eval()
+    x = _image((1, 3, 64, 64), 9).to(cuda).half()
+    n0 = _lib.launch_count()
+    m(x)
+    torch.cuda.synchronize()
+    built = _lib.launch_count() - n0
+    n_convs = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.Conv2d))
+    assert built >= n_convs + 60  # >= one fold_pack per conv (+ stacked C3 halves, per-anchor head rows) + the forward itself

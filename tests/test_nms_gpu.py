@@ -25,6 +25,8 @@ def _run(pred_np, dtype, dev, **kw):
 def test_golden_regimes_bit_exact(cuda):
     g = np.load(os.path.join(G, "nms.npz"))
     for c in json.loads(str(g["meta"])):
+        if c.get("labels"):
+            continue  # test_apriori_labels_bit_exact
         pred = nms_ref.synth_predictions(c["bs"], c["n"], c["nc"], c["nm"], c["seed"], c["dtype"])
         got, gidx = _run(pred, c["dtype"], cuda, **c["kw"])
         _, oidx = nms_ref.non_max_suppression(pred, dtype=c["dtype"], return_index=True, **c["kw"])
@@ -33,6 +35,21 @@ def test_golden_regimes_bit_exact(cuda):
             assert got[b].shape == ref.shape, (c["tag"], b, got[b].shape, ref.shape)
             assert np.array_equal(gidx[b], oidx[b]), (c["tag"], b, "indices")
             assert np.array_equal(got[b], ref), (c["tag"], b, np.abs(got[b] - ref).max())
+
+
+def test_apriori_labels_bit_exact(cuda):
+    """`labels=` (val.py --save-hybrid, reference utils/general.py:706-712): rows and candidate ids vs the oracle and the
+    reference-generated fixture, fp16 and fp32 inputs (an image with labels is processed in fp32 like the reference's cat)."""
+    g = np.load(os.path.join(G, "nms.npz"))
+    for c in [m for m in json.loads(str(g["meta"])) if m.get("labels")]:
+        pred = nms_ref.synth_predictions(c["bs"], c["n"], c["nc"], c["nm"], c["seed"], c["dtype"])
+        labels = [g[f"{c['tag']}.labels{b}"] for b in range(c["bs"])]
+        t = torch.from_numpy(pred).to(cuda, TDT[c["dtype"]])
+        out, idx = non_max_suppression(t, labels=[torch.from_numpy(l).to(cuda) for l in labels], return_indices=True, **c["kw"])
+        _, oidx = nms_ref.non_max_suppression(pred, dtype=c["dtype"], labels=labels, return_index=True, **c["kw"])
+        for b in range(c["bs"]):
+            assert np.array_equal(idx[b].cpu().numpy(), oidx[b]), (c["tag"], b)
+            assert np.array_equal(out[b].cpu().numpy(), g[f"{c['tag']}.{b}"]), (c["tag"], b)
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "fp32"])

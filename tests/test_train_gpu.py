@@ -245,11 +245,12 @@ def _ref_train_step(cfg, sd, img, targets, dev, autocast_dtype):
     return [q.detach() for q in p], loss.detach(), grads
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_model_training_step_yolov5n(cuda, dtype):
-    """DetectionModel('yolov5n').train(): raw head maps, loss and parameter gradients of one step vs the fp32 oracle,
-    judged against torch's own autocast execution of the reference expressions."""
-    name, shape = "yolov5n", (4, 3, 128, 128)
+@pytest.mark.parametrize("name,shape,dtype", [("yolov5n", (4, 3, 128, 128), torch.float16), ("yolov5n", (4, 3, 128, 128), torch.bfloat16),
+                                              ("yolov5m", (2, 3, 192, 256), torch.float16)])
+def test_model_training_step_vs_oracle_amp_yardstick(cuda, name, shape, dtype):
+    """DetectionModel(name).train(): raw head maps, loss and parameter gradients of one step vs the fp32 oracle,
+    judged against torch's own autocast execution of the reference expressions.  yolov5m is BASELINE config 4's model
+    (channel counts 48 / 96 / 192 ...: K tails, odd N tiles in the weight-gradient kernel)."""
     cfg = model_cfg(name)
     sd = model_ref.synth_state_dict(cfg, seed=21)
     g = torch.Generator().manual_seed(22)
@@ -295,7 +296,7 @@ def test_model_training_step_yolov5n(cuda, dtype):
     summary = dict(n=len(ratios), median=ratios[len(ratios) // 2], worst=worst, total_mine=(mine_sq / ref_sq) ** 0.5,
                    total_amp=(amp_sq / ref_sq) ** 0.5)
     print("train-step gradient report", dtype, summary)
-    assert len(ratios) > 150, summary
+    assert len(ratios) > (150 if name == "yolov5n" else 200), summary
     assert worst[0] <= 2.5 and summary["median"] <= 1.25, summary
     assert summary["total_mine"] <= 1e-3 + 1.5 * summary["total_amp"], summary
 
@@ -346,7 +347,9 @@ def test_graphed_train_step_matches_eager(cuda):
         m.load_state_dict(sd)
         m = m.to(cuda).train()
         m.hyp = dict(HYP_SCRATCH_LOW)
-        return m, ComputeLoss(m), torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
+        from yolov5_b200.utils.torch_utils import FusedSGD
+
+        return m, ComputeLoss(m), FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
 
     m1, loss1, opt1 = make()
     items_eager = []
@@ -354,10 +357,9 @@ def test_graphed_train_step_matches_eager(cuda):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             p = m1(img)
         loss, items = loss1(p, tgt)
-        opt1.zero_grad()
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(m1.parameters(), max_norm=10.0)
-        opt1.step()
+        opt1.fused_step(max_norm=10.0)  # clip + SGD in the fused step (bf16: no loss scaling)
+        opt1.zero_grad()
         items_eager.append(items.clone())
     m2, loss2, opt2 = make()
     step = GraphedTrainStep(m2, loss2, opt2, batch=2, size=64, max_targets=96, amp_dtype=torch.bfloat16)
@@ -393,10 +395,11 @@ def test_training_with_a_model_cast_to_bf16(cuda):
 
 
 def test_training_step_against_the_real_reference_fixture(cuda):
-    """tests/golden/train_step.npz = the real reference's training step (fp32, CPU): the engine under fp16 autocast must
-    land within low-precision distance of it -- head maps, loss, BN running statistics, gradients.  (Tight, yardstick-based
-    gradient parity is test_model_training_step_yolov5n; this one ties the engine to numbers the reference itself
-    produced, so the bounds are those of fp16 training noise: a few percent on individual gradient tensors.)"""
+    """tests/golden/train_step.npz = the real reference's training step (fp32, CPU).  The engine under fp16 autocast is a
+    low-precision evaluation of it; so is torch's own autocast execution of the reference expressions.  Both are measured
+    against the fixture on the same inputs and the engine must not be further from the reference's numbers than
+    1e-3 + 1.5 x (torch-AMP's own distance) on head maps / loss / BN statistics / the total gradient, and never more than
+    2.5 x on a single gradient tensor (single-sample noise; same criterion as the yardstick test above)."""
     import os
 
     import numpy as np
@@ -407,6 +410,7 @@ def test_training_step_against_the_real_reference_fixture(cuda):
     sd = model_ref.synth_state_dict(cfg, seed=seed)
     x = torch.from_numpy(np.random.RandomState(seed_x).uniform(0, 1, shape).astype(np.float32))
     targets = torch.from_numpy(loss_ref.synth_targets(shape[0], seed=seed_t)).float()
+    pamp, lossamp, gamp = _ref_train_step(cfg, sd, x, targets, cuda, torch.float16)  # torch autocast, same expressions
     m = DetectionModel("yolov5n")
     m.load_state_dict(sd)
     m = m.to(cuda).train()
@@ -416,24 +420,36 @@ def test_training_step_against_the_real_reference_fixture(cuda):
     rep = {}
     for l, q in enumerate(p):
         ref = torch.from_numpy(g[f"raw{l}"])
-        rep[f"raw{l}"] = float((q.detach().float().cpu() - ref).abs().max()) / float(ref.abs().max())
+        sc = float(ref.abs().max())
+        rep[f"raw{l}"] = (float((q.detach().float().cpu() - ref).abs().max()) / sc, float((pamp[l].float().cpu() - ref).abs().max()) / sc)
     loss, items = ComputeLoss(m)(p, targets.to(cuda))
-    rep["loss"] = abs(float(loss) - float(g["loss"][0])) / float(g["loss"][0])
+    lref = float(g["loss"][0])
+    rep["loss"] = (abs(float(loss) - lref) / lref, abs(float(lossamp) - lref) / lref)
     loss.backward()
     named = dict(m.named_parameters())
+    ratios = []
     for key in g.files:
         if key.startswith("grad."):
             ref = torch.from_numpy(g[key])
-            rep[key] = float((named[key[5:]].grad.float().cpu() - ref).norm()) / float(ref.norm())
+            n = float(ref.norm())
+            e, el = float((named[key[5:]].grad.float().cpu() - ref).norm()) / n, float((gamp[key[5:]].float().cpu() - ref).norm()) / n
+            rep[key] = (e, el)
+            ratios.append(e / (1e-3 + el))
         elif key.startswith("stat."):
             ref = torch.from_numpy(g[key])
-            rep[key] = float((m.state_dict()[key[5:]].float().cpu() - ref).abs().max()) / float(ref.abs().max())
+            rep[key] = (float((m.state_dict()[key[5:]].float().cpu() - ref).abs().max()) / float(ref.abs().max()), None)
     tot = sum(float(g[k][0]) ** 2 for k in g.files if k.startswith("gnorm.")) ** 0.5
     mine = sum(float(q.grad.float().norm()) ** 2 for q in m.parameters()) ** 0.5
-    rep["total_grad_norm"] = abs(mine - tot) / tot
-    print("engine vs reference fixture:", {k: f"{v:.2e}" for k, v in rep.items()})
-    assert all(rep[f"raw{l}"] <= 4e-2 for l in range(3)), rep  # fp16 through ~25 batch-normalised layers: 1-2 % of max at P5
-    assert rep["loss"] <= 1e-2, rep
-    assert all(v <= 0.35 for k, v in rep.items() if k.startswith("grad.")), rep
-    assert all(v <= 5e-2 for k, v in rep.items() if k.startswith("stat.")), rep
-    assert rep["total_grad_norm"] <= 0.1, rep
+    amp = sum(float(v.float().norm()) ** 2 for v in gamp.values()) ** 0.5
+    rep["total_grad_norm"] = (abs(mine - tot) / tot, abs(amp - tot) / tot)
+    ratios.sort()
+    print("engine vs reference fixture (mine, torch-AMP):", {k: tuple(None if t is None else float(f"{t:.2e}") for t in v) for k, v in rep.items()},
+          "gradient ratio median / max:", ratios[len(ratios) // 2], ratios[-1])
+    for k, (e, el) in rep.items():
+        if k.startswith("stat."):
+            assert e <= 5e-2, (k, e)  # running statistics: momentum 0.03 x batch statistics of fp16 activations
+        elif k.startswith("grad."):
+            assert e <= 1e-3 + 2.5 * el, (k, e, el)
+        else:
+            assert e <= 1e-3 + 1.5 * el, (k, e, el)
+    assert ratios[len(ratios) // 2] <= 1.25, ratios

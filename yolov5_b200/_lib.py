@@ -87,6 +87,23 @@ class WgradDesc(C.Structure):
     ]
 
 
+class LetterboxImage(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p), ("src_h", C.c_int32), ("src_w", C.c_int32), ("row_bytes", C.c_int32),
+        ("new_h", C.c_int32), ("new_w", C.c_int32), ("top", C.c_int32), ("left", C.c_int32),
+    ]
+
+
+class OptTensor(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("mom", C.c_void_p), ("ema", C.c_void_p),
+        ("numel", C.c_int64), ("group", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+# indices into the fused optimizer's `hyper` array (include/y5b200.h Y5_OPT_*)
+OPT_INV_SCALE, OPT_MAX_NORM, OPT_EMA_DECAY, OPT_EMA_TAU, OPT_EMA_UPDATES, OPT_OUT_NORM, OPT_OUT_SKIPPED, OPT_GROUPS = 0, 1, 2, 3, 4, 5, 6, 8
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 # name -> (restype, argtypes); mirrors include/y5b200.h one to one (tests/test_abi.py checks the header against this)
@@ -126,6 +143,19 @@ SIGNATURES = {
     "y5_col_sum": (_I32, [_P, _I32, _I64, _I32, _I32, _P, _P, _P]),
     "y5_weight_pack": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "y5_zero_stuff2x": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "y5_loss_fwd_bwd_scaled": (_I32, [C.POINTER(LossParams), C.POINTER(_P), _P, _P, _P, C.POINTER(_P), _P, _P, _I64, _P]),
+    "y5_letterbox_max_images": (_I32, []),
+    "y5_letterbox": (_I32, [C.POINTER(LetterboxImage), _I32, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _I32, _P]),
+    "y5_process_mask_workspace_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "y5_process_mask": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _I32, _I32, C.POINTER(_I32), _P, _I32, _P, _I64,
+                                _P]),
+    "y5_crop_mask": (_I32, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "y5_scale_boxes": (_I32, [_P, _I32, _I64, _P, _I32, _P, _P, _P]),
+    "y5_labels_native": (_I32, [_P, _I32, _P, _P, _P]),
+    "y5_match_batch": (_I32, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _P, _I32, _F, _P, _P]),
+    "y5_opt_chunk_elems": (_I32, []),
+    "y5_opt_step": (_I32, [_P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P]),
+    "y5_fold_pack": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _I32, _I32, _P, _I32, _P]),
 }
 
 _lib = None
@@ -157,6 +187,12 @@ def check(code: int, what: str = "") -> None:
 
 def stream_ptr(device=None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def on(device):
+    """Device guard for the entry points: the C ABI launches on the CURRENT CUDA device, so a model / tensor living on
+    cuda:1 while cuda:0 is current must switch first (per-device kernel attributes are handled inside the library)."""
+    return torch.cuda.device(device)
 
 
 def launch_count() -> int:

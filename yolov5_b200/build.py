@@ -29,6 +29,8 @@ SOURCES = {
     "train_kernels.cu": [],
     "nms.cu": ["-fmad=false"],
     "loss.cu": ["-fmad=false"],
+    "post_kernels.cu": ["-fmad=false"],
+    "optim_kernels.cu": [],
 }
 
 

@@ -262,8 +262,8 @@ extern "C" Y5_API int y5_sppf_pool(const void* x, int32_t x_pitch, void* y1, voi
     if (c % 8 || x_pitch % 8 || y_pitch % 8 || !half_dtype(dtype) || !(ksize & 1)) return set_error(Y5_E_UNSUPPORTED, "sppf_pool: c/pitch %% 8, odd k, fp16/bf16 only");
     const size_t smem = static_cast<size_t>(2) * h * w * sizeof(uint4);
     if (smem <= 96 * 1024 && static_cast<long long>(batch) * (c / 8) < 0x7fffffff) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(sppf_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+        if (ensure_dyn_smem(reinterpret_cast<const void*>(sppf_pool_smem_kernel), 96 * 1024) != cudaSuccess)
+            return set_error(Y5_E_DRIVER, "sppf_pool: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         sppf_pool_smem_kernel<<<batch * (c / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const uint16_t*>(x), x_pitch, static_cast<uint16_t*>(y1), static_cast<uint16_t*>(y2), static_cast<uint16_t*>(y3),
             y_pitch, h, w, c, ksize, dtype == Y5_BF16);

@@ -565,11 +565,7 @@ void pick_tile(int out_c, int a_mode, int k_total, int64_t m_tiles, int* block_n
 
 template <int BN, int EPI, int MT>
 cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, int cluster, uint32_t smem, cudaStream_t st) {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
+    const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_kernel<BN, EPI, MT>), 227 * 1024);
     if (attr_err != cudaSuccess) return attr_err;
     count_launch();
     static const bool pdl = [] { const char* e = getenv("Y5_PDL"); return !(e && e[0] == '0'); }();

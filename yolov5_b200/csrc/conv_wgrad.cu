@@ -311,9 +311,7 @@ extern "C" Y5_API int y5_conv_wgrad(const y5_wgrad_desc* d, void* stream) {
         if (me != cudaSuccess) return set_error(int(me), "wgrad: memset failed: %s", cudaGetErrorString(me));
     }
     const uint32_t smem = p.stages * p.stage_bytes + (2 * kWgStagesMax + 1) * 8 + 16 + 1024;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_kernel), 227 * 1024);
     if (attr_err != cudaSuccess) return set_error(int(attr_err), "wgrad: cudaFuncSetAttribute failed");
     const long long grid = items * p.splits;
     count_launch();

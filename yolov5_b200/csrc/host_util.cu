@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <set>
+#include <utility>
 
 #include "../../include/y5b200.h"
 #include "host_util.h"
@@ -21,13 +23,29 @@ int set_error(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
-    static int n = 0;
+    static int per_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = per_dev[dev];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        per_dev[dev] = n;
     }
     return n;
+}
+
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(kernel, dev);
+    if (done.count(key)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.insert(key);
+    return e;
 }
 
 static void* driver_entry(const char* name) {

@@ -31,6 +31,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and one process
+// may drive several GPUs (DataParallel, a model on cuda:1 while cuda:0 is current ...)
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes);
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -32,6 +32,7 @@ struct LossArgs {
     const float* targets;
     const float* anchors;
     float anchor_t, box_gain, obj_gain, cls_gain, cls_pw, obj_pw, cp, cn, grad_scale;
+    const float* grad_scale_dev;              // optional upstream gradient of the loss (device scalar), multiplied in fp32
     float balance[kMaxLevels];
     int cap;                                  // matches capacity per level = 5*na*nt
     int* count;                               // [nl]
@@ -116,6 +117,9 @@ __global__ void loss_targets_kernel(LossArgs a) {
             if (ok) {
                 b = static_cast<int>(tg[0]);    // .long(): truncation
                 cls = static_cast<int>(tg[1]);
+                // the reference raises IndexError for an image index >= batch or a class >= nc; a kernel cannot, and must
+                // not write out of bounds: such rows are ignored
+                if (b < 0 || b >= a.B || cls < 0 || cls >= a.nc) ok = false;
                 const int ix = static_cast<int>(__fsub_rn(gx, ox)), iy = static_cast<int>(__fsub_rn(gy, oy));
                 gi = min(max(ix, 0), nx - 1);   // clamp_ aliases gij (:242), so tbox below uses the clamped cell
                 gj = min(max(iy, 0), ny - 1);
@@ -241,7 +245,8 @@ __global__ void loss_dense_kernel(LossArgs a) {
     const int l = blockIdx.y;
     const long long total = a.cells[l] * a.no;
     // d(loss*bs*grad_scale)/d obj logit = obj_gain * balance / cells * bs * grad_scale * dBCE
-    const float gscale = a.obj_gain * a.balance[l] * static_cast<float>(a.B) * a.grad_scale / static_cast<float>(a.cells[l]);
+    const float up = a.grad_scale_dev ? *a.grad_scale_dev : 1.0f;
+    const float gscale = a.obj_gain * a.balance[l] * static_cast<float>(a.B) * a.grad_scale * up / static_cast<float>(a.cells[l]);
     float local = 0.0f;
     const bool want_grad = a.grad[l] != nullptr;
     for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
@@ -279,7 +284,7 @@ __global__ void loss_cls_kernel(LossArgs a) {
     const int wpb = blockDim.x >> 5;
     const bool want_grad = a.grad[l] != nullptr;
     // lbox_l = mean(1-iou): each match contributes 1/n; lcls_l = mean over n*nc
-    const float fb = static_cast<float>(a.B) * a.grad_scale;
+    const float fb = static_cast<float>(a.B) * a.grad_scale * (a.grad_scale_dev ? *a.grad_scale_dev : 1.0f);
     const float gbox = n > 0 ? a.box_gain * fb / static_cast<float>(n) : 0.f;
     const float gcls = n > 0 ? a.cls_gain * fb / (static_cast<float>(n) * static_cast<float>(a.nc)) : 0.f;
     float local = 0.0f;
@@ -397,6 +402,12 @@ extern "C" Y5_API int64_t y5_loss_workspace_bytes(const y5_loss_params* p) {
 
 extern "C" Y5_API int y5_loss_fwd_bwd(const y5_loss_params* p, const void* const* pl, const float* targets, const float* anchors,
                                       float* out_loss, void* const* grad, void* workspace, int64_t workspace_bytes, void* stream) {
+    return y5_loss_fwd_bwd_scaled(p, pl, targets, anchors, out_loss, grad, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" Y5_API int y5_loss_fwd_bwd_scaled(const y5_loss_params* p, const void* const* pl, const float* targets, const float* anchors,
+                                             float* out_loss, void* const* grad, const float* grad_scale_dev, void* workspace,
+                                             int64_t workspace_bytes, void* stream) {
     if (int e = validate_loss(p)) return e;
     if (!pl || !anchors || !out_loss || !workspace || (p->nt > 0 && !targets)) return set_error(Y5_E_INVALID, "loss: null pointer");
     const LossWs L = loss_ws(p);
@@ -410,6 +421,7 @@ extern "C" Y5_API int y5_loss_fwd_bwd(const y5_loss_params* p, const void* const
         a.grad[l] = grad ? grad[l] : nullptr;
     }
     a.targets = targets; a.anchors = anchors; a.out_loss = out_loss;
+    a.grad_scale_dev = grad_scale_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     loss_zero_kernel<<<sms * 4, 256, 0, st>>>(a);

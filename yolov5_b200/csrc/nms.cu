@@ -613,12 +613,9 @@ extern "C" Y5_API int y5_nms_batched(const y5_nms_params* p, const void* pred, f
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int threads = 256, wpb = threads / 32;
     dim3 grid((nseg + wpb - 1) / wpb, p->batch);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCandCap * 6);
-        cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDetCap * 20);
-        attr_done = true;
-    }
+    if (ensure_dyn_smem(reinterpret_cast<const void*>(nms_sort_kernel), kCandCap * 6) != cudaSuccess ||
+        ensure_dyn_smem(reinterpret_cast<const void*>(nms_greedy_kernel), kMaxDetCap * 20) != cudaSuccess)
+        return set_error(Y5_E_DRIVER, "nms: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
     nms_pass_kernel<0><<<grid, threads, 0, st>>>(a, 0);
     nms_scan_kernel<0><<<p->batch, 1024, 0, st>>>(a);
     int launches = 2;

@@ -393,6 +393,49 @@ __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, in
     }
 }
 
+
+// eval-mode BatchNorm folded into the conv weights + K-major packing, one launch (reference utils/torch_utils.py:224-254):
+// scale = gamma / sqrt(var + eps) in fp32 (same operation order as torch's expression), W' = W * scale rounded once to the
+// activation dtype, b' = beta + (b - mean) * scale in fp32.
+__device__ __forceinline__ float load_any(const void* p, long long i, int dtype) {
+    if (dtype == Y5_F32) return static_cast<const float*>(p)[i];
+    return unpack1(static_cast<const uint16_t*>(p)[i], dtype == Y5_BF16);
+}
+__global__ void fold_pack_kernel(const void* __restrict__ w, int w_dtype, int cout, int cin, int kh, int kw, const void* __restrict__ cbias,
+                                 const void* __restrict__ gamma, const void* __restrict__ beta, const void* __restrict__ mean,
+                                 const void* __restrict__ var, int bn_dtype, float eps, uint16_t* __restrict__ packed, int ci_pad, int co_pad,
+                                 float* __restrict__ bias_out, int bf16) {
+    const long long n = static_cast<long long>(co_pad) * kh * kw * ci_pad;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % ci_pad);
+        long long t = i / ci_pad;
+        const int s_ = static_cast<int>(t % kw);
+        t /= kw;
+        const int r = static_cast<int>(t % kh);
+        const int co = static_cast<int>(t / kh);
+        float v = 0.f;
+        if (ci < cin && co < cout) {
+            v = load_any(w, ((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s_, w_dtype);
+            if (gamma) v = __fmul_rn(v, __fdiv_rn(load_any(gamma, co, bn_dtype), __fsqrt_rn(__fadd_rn(load_any(var, co, bn_dtype), eps))));
+        }
+        packed[i] = pack1(v, bf16 != 0);
+    }
+    if (bias_out)
+        for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < co_pad; co += gridDim.x * blockDim.x) {
+            float b = 0.f;
+            if (co < cout) {
+                const float b0 = cbias ? load_any(cbias, co, w_dtype) : 0.f;
+                if (gamma) {
+                    const float sc = __fdiv_rn(load_any(gamma, co, bn_dtype), __fsqrt_rn(__fadd_rn(load_any(var, co, bn_dtype), eps)));
+                    b = __fadd_rn(load_any(beta, co, bn_dtype), __fmul_rn(__fsub_rn(b0, load_any(mean, co, bn_dtype)), sc));
+                } else {
+                    b = b0;
+                }
+            }
+            bias_out[co] = b;
+        }
+}
+
 // backward of nn.Upsample(scale_factor=2, 'nearest'): dx[n,y,x,:] = sum of the 2x2 block of dy (fp32 sum, one rounding)
 __global__ void upsample2x_bwd_kernel(const void* __restrict__ dy, int dy_pitch, void* __restrict__ dx, int dx_pitch, int B, int H, int W, int C,
                                       int bf16) {
@@ -586,6 +629,25 @@ extern "C" Y5_API int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out
     launch_pdl(weight_pack_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), w, w_dtype, out_c, in_c, ksize, static_cast<uint16_t*>(fwd), in_c_pad,
                                                                               static_cast<uint16_t*>(dgrad), out_c_pad, dtype == Y5_BF16);
     return launch_status("weight_pack");
+}
+
+
+extern "C" Y5_API int y5_fold_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t kh, int32_t kw, const void* conv_bias,
+                                   const void* gamma, const void* beta, const void* mean, const void* var, int32_t bn_dtype, float eps,
+                                   void* packed, int32_t in_c_pad, int32_t out_c_pad, float* bias_out, int32_t dtype, void* stream) {
+    if (!w || !packed) return set_error(Y5_E_INVALID, "fold_pack: null pointer");
+    if (w_dtype != Y5_F32 && w_dtype != Y5_F16 && w_dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "fold_pack: weight dtype");
+    if (bn_dtype != Y5_F32 && bn_dtype != Y5_F16 && bn_dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "fold_pack: BatchNorm dtype");
+    if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "fold_pack: packed dtype must be fp16 or bf16");
+    if (out_c <= 0 || in_c <= 0 || kh <= 0 || kw <= 0 || in_c_pad < in_c || out_c_pad < out_c) return set_error(Y5_E_INVALID, "fold_pack: bad shape");
+    if (gamma && (!beta || !mean || !var)) return set_error(Y5_E_INVALID, "fold_pack: BatchNorm needs gamma, beta, mean and var");
+    const long long total = static_cast<long long>(out_c_pad) * kh * kw * in_c_pad;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 8));
+    count_launch();
+    fold_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w_dtype, out_c, in_c, kh, kw, conv_bias, gamma, beta, mean, var,
+                                                                            bn_dtype, eps, static_cast<uint16_t*>(packed), in_c_pad, out_c_pad,
+                                                                            bias_out, dtype == Y5_BF16);
+    return launch_status("fold_pack");
 }
 
 extern "C" Y5_API int y5_upsample2x_bwd(const void* dy, int32_t dy_pitch, void* dx, int32_t dx_pitch, int32_t batch, int32_t h, int32_t w, int32_t c,

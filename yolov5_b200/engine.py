@@ -135,26 +135,80 @@ class Program:
         return View(self.new_buf(h, w, c), 0, c)
 
     # ------------------------------------------------------------------ op emitters
-    def conv(self, x: View, out: View, w_fp32: torch.Tensor, b_fp32: torch.Tensor, k: int, s: int, p: int, act: bool,
-             residual: View | None = None, name: str = "conv", virt=None):
-        """Emit one fused conv.  `virt` (stem only) = dict(ptr, in_c, in_w, in_h, x_stride, y_stride, n_stride, kw, pad_w):
-        a strided "wide pixel" view of the input and a non-square filter, see y5_conv_desc in include/y5b200.h."""
+    def block_k(self, cin: int, cout: int, m_rows: int) -> int:
+        bk = C.c_int32()
+        _lib.check(self.lib.y5_conv_pick(cin, cout, m_rows, C.byref(bk), None), "conv_pick")
+        return bk.value
+
+    def fold_pack(self, parts, m_rows: int):
+        """Folded + packed weights of one GEMM from module parameters, one y5_fold_pack launch per part (no ATen arithmetic).
+        parts: list of (weight (O,I,kh,kw) tensor, conv bias | None, bn | None); several parts stack along the output channels
+        (C3's cv1 | cv2).  Returns (packed [sum O][kh][kw][I_pad] in the activation dtype, fp32 bias [sum O], block_k)."""
+        cin, kh, kw = parts[0][0].shape[1:]
+        cout = sum(w.shape[0] for w, _, _ in parts)
+        bk = self.block_k(cin, cout, m_rows)
+        ipad = (cin + bk - 1) // bk * bk
+        wp = torch.empty(cout, kh, kw, ipad, dtype=self.dtype, device=self.device)
+        bias = torch.empty(cout, dtype=torch.float32, device=self.device)
+        self.fold_pack_into(parts, wp, bias, 0, ipad)
+        return wp, bias, bk
+
+    def fold_pack_into(self, parts, wp, bias, row0: int, ipad: int, pad_rows_to: int | None = None):
+        st = C.c_void_p(_lib.stream_ptr(self.device))
+        es = wp.element_size()
+        for w, cb, bn in parts:
+            w = w.detach()
+            if not w.is_contiguous():
+                w = w.contiguous()
+            if w.device != self.device:
+                raise RuntimeError("y5b200: module parameters and the input must live on the same CUDA device")
+            o, i, kh, kw = w.shape
+            rows = pad_rows_to or o
+            keep = [w]
+            if cb is not None:
+                cb = cb.detach().to(w.dtype).contiguous()
+                keep.append(cb)
+            g = b_ = mu = var = None
+            bn_code, eps = _lib.Y5_F32, 0.0
+            if bn is not None:
+                g, b_, mu, var = (t.detach().contiguous() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+                if not (g.dtype == b_.dtype == mu.dtype == var.dtype):
+                    g, b_, mu, var = g.float(), b_.float(), mu.float(), var.float()
+                bn_code, eps = _lib.dtype_code(g.dtype), float(bn.eps)
+                keep += [g, b_, mu, var]
+            _lib.check(self.lib.y5_fold_pack(w.data_ptr(), _lib.dtype_code(w.dtype), o, i, kh, kw, cb.data_ptr() if cb is not None else None,
+                                             g.data_ptr() if g is not None else None, b_.data_ptr() if b_ is not None else None,
+                                             mu.data_ptr() if mu is not None else None, var.data_ptr() if var is not None else None, bn_code, eps,
+                                             wp.data_ptr() + row0 * kh * kw * ipad * es, ipad, rows, bias.data_ptr() + row0 * 4, self.dt_code, st),
+                       "fold_pack")
+            self._keep += keep  # the launch is asynchronous: temporaries must outlive it
+            row0 += rows
+
+    def conv(self, x: View, out: View, w_fp32, b_fp32, k: int, s: int, p: int, act: bool,
+             residual: View | None = None, name: str = "conv", virt=None, packed=None):
+        """Emit one fused conv.  Weights come either as fp32 tensors (w_fp32 OIHW already folded, b_fp32) that are packed here,
+        or pre-packed by fold_pack: packed = (wp, bias, block_k, cin).  `virt` (stem only) = dict(ptr, in_c, in_w, in_h, x_stride,
+        y_stride, n_stride, kw, pad_w): a strided "wide pixel" view of the input and a non-square filter, see y5_conv_desc in
+        include/y5b200.h."""
         cout = out.c
         if virt is None:
             cin, in_h, in_w, kw = x.c, x.h, x.w, k
-            assert w_fp32.shape == (cout, cin, k, k), (w_fp32.shape, cout, cin, k)
             ho, wo = (x.h + 2 * p - k) // s + 1, (x.w + 2 * p - k) // s + 1
         else:
             cin, in_h, in_w, kw = virt["in_c"], virt["in_h"], virt["in_w"], virt["kw"]
-            assert w_fp32.shape == (cout, cin, k, kw), (w_fp32.shape, cout, cin, k, kw)
             ho, wo = (in_h + 2 * p - k) // s + 1, (in_w + 2 * virt["pad_w"] - kw) // s + 1
         assert (ho, wo) == (out.h, out.w), (name, ho, wo, out.h, out.w)
         m_rows = self.B * ho * wo
         bk, bn = C.c_int32(), C.c_int32()
-        _lib.check(self.lib.y5_conv_pick(cin, cout, m_rows, C.byref(bk), C.byref(bn)), "conv_pick")
         bn.value = int(os.environ.get("Y5_FORCE_BLOCK_N", "0"))  # 0: the library's tile cost model decides (block_n, MT)
-        wp = pack_weight(w_fp32, bk.value, self.dtype)
-        bias = b_fp32.to(torch.float32).contiguous()
+        if packed is None:
+            assert w_fp32.shape == (cout, cin, k, kw), (w_fp32.shape, cout, cin, k, kw)
+            bk.value = self.block_k(cin, cout, m_rows)
+            wp = pack_weight(w_fp32, bk.value, self.dtype)
+            bias = b_fp32.to(torch.float32).contiguous()
+        else:
+            wp, bias, bk.value, pc = packed
+            assert pc == cin and wp.shape[0] == cout and wp.shape[1:3] == (k, kw), (name, wp.shape, cout, cin, k, kw)
         self._keep += [wp, bias]
         d = ConvDesc()
         if virt is None:
@@ -185,14 +239,15 @@ class Program:
 
     def conv_module(self, m, x: View, out: View, residual: View | None = None, name="conv"):
         """m: models.common.Conv (conv + bn + act) in its fused or unfused state."""
-        w, b = fold_conv_bn(m.conv, getattr(m, "bn", None))
         k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
         act = isinstance(m.act, torch.nn.SiLU)
         if not act and not isinstance(m.act, torch.nn.Identity):
             raise NotImplementedError(f"y5b200: activation {type(m.act).__name__} (only SiLU / Identity are built)")
         if m.conv.groups != 1 or m.conv.dilation[0] != 1:
             raise NotImplementedError("y5b200: grouped / dilated convolutions are outside the YOLOv5 n..x hot path")
-        self.conv(x, out, w, b, k, s, p, act, residual, name)
+        ho, wo = (x.h + 2 * p - k) // s + 1, (x.w + 2 * p - k) // s + 1
+        wp, bias, bk = self.fold_pack([(m.conv.weight, m.conv.bias, getattr(m, "bn", None))], self.B * ho * wo)
+        self.conv(x, out, None, None, k, s, p, act, residual, name, packed=(wp, bias, bk, x.c))
 
     def out_hw(self, m, x: View):
         k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
@@ -245,9 +300,9 @@ class Program:
         c_ = m.cv1.conv.out_channels
         cat = self.new_view(x.h, x.w, 2 * c_)
         # cv1 | cv2 stacked along the output channels: one GEMM, result is already the concat layout
-        w1, b1 = fold_conv_bn(m.cv1.conv, getattr(m.cv1, "bn", None))
-        w2, b2 = fold_conv_bn(m.cv2.conv, getattr(m.cv2, "bn", None))
-        self.conv(x, cat, torch.cat((w1, w2), 0), torch.cat((b1, b2), 0), 1, 1, 0, True, None, f"{name}.cv1|cv2")
+        wp, bias, bk = self.fold_pack([(m.cv1.conv.weight, m.cv1.conv.bias, getattr(m.cv1, "bn", None)),
+                                       (m.cv2.conv.weight, m.cv2.conv.bias, getattr(m.cv2, "bn", None))], self.B * x.h * x.w)
+        self.conv(x, cat, None, None, 1, 1, 0, True, None, f"{name}.cv1|cv2", packed=(wp, bias, bk, x.c))
         a = cat.slice(0, c_)
         if len(m.m):
             tmp = self.new_view(x.h, x.w, c_)
@@ -297,16 +352,16 @@ class Program:
             HEAD_N = 128  # kHeadN in conv_gemm.cu: one anchor per 128-wide N tile
             if no > HEAD_N:
                 raise NotImplementedError(f"y5b200: Detect with no={no} > {HEAD_N} outputs per anchor")
-            w = conv.weight.detach().float()  # (na*no, C, 1, 1)
-            bk = C.c_int32()
-            _lib.check(self.lib.y5_conv_pick(v.c, na * no, self.B * v.h * v.w, C.byref(bk), None), "conv_pick")
-            wpad = torch.zeros(na, HEAD_N, v.c, 1, 1, dtype=w.dtype, device=w.device)
-            wpad[:, :no] = w.view(na, no, v.c, 1, 1)
-            wp = pack_weight(wpad.view(na * HEAD_N, v.c, 1, 1), bk.value, self.dtype)
-            bias = torch.zeros(na, HEAD_N, dtype=torch.float32, device=w.device)
-            bias[:, :no] = conv.bias.detach().float().view(na, no)
-            bias = bias.view(-1).contiguous()
-            self._keep += [wp, bias]
+            # every anchor's `no` rows padded to HEAD_N: one fold_pack launch per anchor (weights + bias, no BatchNorm)
+            bk = C.c_int32(self.block_k(v.c, na * no, self.B * v.h * v.w))
+            ipad = (v.c + bk.value - 1) // bk.value * bk.value
+            wp = torch.empty(na * HEAD_N, 1, 1, ipad, dtype=self.dtype, device=self.device)
+            bias = torch.empty(na * HEAD_N, dtype=torch.float32, device=self.device)
+            w4 = conv.weight.detach().contiguous().view(na, no, v.c, 1, 1)
+            b2 = conv.bias.detach().contiguous().view(na, no)
+            for a_i in range(na):
+                self.fold_pack_into([(w4[a_i], b2[a_i], None)], wp, bias, a_i * HEAD_N, ipad, pad_rows_to=HEAD_N)
+            self._keep += [wp, bias, w4, b2]
             d = DetectDesc()
             d.inp, d.in_pitch = v.ptr, v.pitch
             d.batch, d.ny, d.nx, d.in_c = self.B, v.h, v.w, v.c

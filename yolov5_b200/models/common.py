@@ -36,14 +36,9 @@ class _EngineLayer(nn.Module):
             with torch.autocast("cuda", enabled=False):
                 return _run(self, x.to(dt), dt)
         key = (tuple(x.shape), x.dtype, x.device.index, _param_version(self))
-        cache = self.__dict__.setdefault("_y5_programs", {})
-        prog = cache.get(key)
-        if prog is None:
-            cache.clear()
-            b, c, h, w = x.shape
-            prog = Program(self, b, h, w, x.dtype, x.device, in_channels=c)
-            cache[key] = prog
-        return prog.run_layer(x)
+        b, c, h, w = x.shape
+        with _lib_on(x.device):
+            return _cached_program(self, key, lambda: Program(self, b, h, w, x.dtype, x.device, in_channels=c)).run_layer(x)
 
     def forward(self, x):
         return self._engine_forward(x)
@@ -51,11 +46,62 @@ class _EngineLayer(nn.Module):
     def __getstate__(self):  # programs hold raw pointers: never pickle them (checkpoints pickle whole modules)
         d = self.__dict__.copy()
         d.pop("_y5_programs", None)
+        d.pop("_y5_tensors", None)
         return d
+
+    def _apply(self, fn, *a, **k):
+        _drop_engine_cache(self)
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        _drop_engine_cache(self)
+        return super().load_state_dict(*a, **k)
+
+
+def _lib_on(device):
+    from .. import _lib
+
+    return _lib.on(device)
 
 
 def _param_version(m: nn.Module) -> int:
-    return sum(p._version for p in m.parameters()) + sum(b._version for b in m.buffers())
+    """In-place edits of parameters / buffers (optimizer steps, BN statistics, manual surgery) invalidate the packed weights
+    of a cached Program.  The tensor list is gathered once per module (walking ~350 sub-modules per forward cost more than the
+    yolov5n forward itself); `_apply` / `load_state_dict` / `fuse` drop it together with the programs."""
+    ts = m.__dict__.get("_y5_tensors")
+    if ts is None:
+        ts = m.__dict__["_y5_tensors"] = list(m.parameters()) + list(m.buffers())
+    v = 0
+    for t in ts:
+        v += t._version
+    return v
+
+
+def _drop_engine_cache(m: nn.Module) -> None:
+    m.__dict__.pop("_y5_programs", None)
+    m.__dict__.pop("_y5_tensors", None)
+
+
+PROGRAM_CACHE = 8  # cached Programs per module (least recently used one is dropped)
+
+
+def _cached_program(m: nn.Module, key, build):
+    from collections import OrderedDict
+
+    cache = m.__dict__.get("_y5_programs")
+    if cache is None:
+        cache = m.__dict__["_y5_programs"] = OrderedDict()
+    prog = cache.get(key)
+    if prog is None:
+        # programs of an older parameter version can never be hit again: drop them first
+        for k in [k for k in cache if k[-1] != key[-1]]:
+            del cache[k]
+        while len(cache) >= PROGRAM_CACHE:
+            cache.popitem(last=False)
+        prog = cache[key] = build()
+    else:
+        cache.move_to_end(key)
+    return prog
 
 
 class Conv(_EngineLayer):

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from ..cfg import model_cfg
-from .common import C3, SPPF, Bottleneck, Concat, Conv, Proto, _param_version  # noqa: F401
+from .common import C3, SPPF, Bottleneck, Concat, Conv, Proto, _cached_program, _drop_engine_cache, _lib_on, _param_version  # noqa: F401
 
 
 def make_divisible(x, divisor):
@@ -132,24 +132,34 @@ def _layer_strides(model: nn.Sequential) -> list[float]:
     return []
 
 
+def scale_img(img, ratio=1.0, same_shape=False, gs=32):
+    """(B,C,H,W) image batch resized by `ratio` (bilinear) and padded right/bottom with the ImageNet grey 0.447 up to a
+    multiple of `gs` -- ultralytics.utils.torch_utils.scale_img as used by the TTA path (reference models/yolo.py:276)."""
+    if ratio == 1.0:
+        return img
+    h, w = img.shape[2:]
+    s = (int(h * ratio), int(w * ratio))
+    img = torch.nn.functional.interpolate(img, size=s, mode="bilinear", align_corners=False)
+    if not same_shape:
+        h, w = (math.ceil(x * ratio / gs) * gs for x in (h, w))
+    return torch.nn.functional.pad(img, [0, w - s[1], 0, h - s[0]], value=0.447)
+
+
 class BaseModel(nn.Module):
     def forward(self, x, profile=False, visualize=False):
-        return self._forward_once(x)
+        return self._forward_once(x, profile, visualize)
 
     def _program(self, x):
         from ..engine import Program
 
         key = (tuple(x.shape), x.dtype, x.device.index, _param_version(self))
-        cache = self.__dict__.setdefault("_y5_programs", {})
-        prog = cache.get(key)
-        if prog is None:
-            if len(cache) >= 4:
-                cache.clear()
-            b, c, h, w = x.shape
+        b, c, h, w = x.shape
+
+        def build():
             dt = x.dtype if x.dtype in (torch.float16, torch.bfloat16) else next(self.parameters()).dtype
-            prog = Program(self, b, h, w, dt, x.device)
-            cache[key] = prog
-        return prog
+            return Program(self, b, h, w, dt, x.device)
+
+        return _cached_program(self, key, build)
 
     def _forward_once(self, x, profile=False, visualize=False):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
@@ -164,8 +174,10 @@ class BaseModel(nn.Module):
         if self.training:  # list of raw (B,na,ny,nx,no) maps with an autograd graph, as models/yolo.py:98 returns
             from ..train_ops import forward_train
 
-            return forward_train(self, x)
-        z, raws, proto = self._program(x).run_model(x)
+            with _lib_on(x.device):
+                return forward_train(self, x)
+        with _lib_on(x.device):
+            z, raws, proto = self._program(x).run_model(x)
         if isinstance(head, Segment):
             return (z, proto) if head.export else (z, proto, raws)
         return (z,) if head.export else (z, raws)
@@ -179,7 +191,7 @@ class BaseModel(nn.Module):
             if isinstance(m, Conv) and hasattr(m, "bn"):
                 m.conv = fuse_conv_and_bn(m.conv, m.bn)
                 delattr(m, "bn")
-        self.__dict__.pop("_y5_programs", None)
+        _drop_engine_cache(self)
         return self
 
     def info(self, verbose=False, img_size=640):
@@ -191,12 +203,17 @@ class BaseModel(nn.Module):
         m = self.model[-1]
         if isinstance(m, Detect) and m.stride is not None:
             m.stride = fn(m.stride)
-        self.__dict__.pop("_y5_programs", None)
+        _drop_engine_cache(self)
         return self
+
+    def load_state_dict(self, *a, **k):
+        _drop_engine_cache(self)
+        return super().load_state_dict(*a, **k)
 
     def __getstate__(self):
         d = self.__dict__.copy()
         d.pop("_y5_programs", None)
+        d.pop("_y5_tensors", None)
         return d
 
 
@@ -234,6 +251,37 @@ class DetectionModel(BaseModel):
             self.stride = m.stride
             self._initialize_biases()
         initialize_weights(self)
+
+    def forward(self, x, augment=False, profile=False, visualize=False):
+        """Same call signature as reference models/yolo.py:263: single-scale inference / training forward, or test-time
+        augmentation over three scales and a left-right flip (`augment=True`)."""
+        if augment:
+            return self._forward_augment(x)
+        return self._forward_once(x, profile, visualize)
+
+    def _forward_augment(self, x):
+        """TTA (reference models/yolo.py:269-283): the engine runs each scaled / flipped copy (one cached Program per
+        shape); de-scaling, de-flipping and the tail clipping are host-side tensor edits on the decoded predictions."""
+        if self.training:
+            raise RuntimeError("y5b200: augment=True is an inference-time option (model.eval())")
+        img_size = x.shape[-2:]
+        gs = int(self.stride.max())
+        if x.dtype == torch.uint8:
+            x = x.to(next(self.parameters()).dtype) / 255
+        ys = []
+        for scale, flip in zip((1, 0.83, 0.67), (None, 3, None)):
+            xi = scale_img(x.flip(flip) if flip else x, scale, gs=gs)
+            yi = self._forward_once(xi)[0]
+            yi[..., :4] /= scale
+            if flip == 3:
+                yi[..., 0] = img_size[1] - yi[..., 0]
+            ys.append(yi)
+        # drop the largest-stride rows of the full-scale copy and the smallest-stride rows of the smallest copy
+        nl = self.model[-1].nl
+        g = sum(4 ** k for k in range(nl))
+        ys[0] = ys[0][:, : ys[0].shape[1] - ys[0].shape[1] // g]
+        ys[-1] = ys[-1][:, (ys[-1].shape[1] // g) * 4 ** (nl - 1) :]
+        return torch.cat(ys, 1), None
 
     def _initialize_biases(self, cf=None):
         """Detect bias prior (reference models/yolo.py:314-327)."""

@@ -19,21 +19,28 @@ def smooth_bce(eps=0.1):
 
 
 class _LossFn(torch.autograd.Function):
+    """loss, items = ComputeLoss(p, targets).  The forward launch set computes the loss only; the backward one re-runs it with
+    the gradient outputs enabled and the UPSTREAM gradient of the loss (GradScaler's factor x WORLD_SIZE x ..., a device
+    scalar) multiplied in fp32 inside the kernels before anything is rounded to the prediction dtype -- exactly where
+    autograd applies it for `scaler.scale(loss).backward()` (reference train.py:410).  Scaling fp16 gradients afterwards
+    would overflow (65536 is not an fp16 number) and would already have flushed small objectness gradients to zero."""
+
     @staticmethod
     def forward(ctx, crit, targets, *p):
-        out, grads = crit._run(p, targets, want_grad=any(t.requires_grad for t in p))
-        ctx.grads = grads
-        ctx.n = len(p)
+        out, _ = crit._run(p, targets, want_grad=False)
+        ctx.crit, ctx.targets = crit, targets
+        ctx.save_for_backward(*p)
         ctx.mark_non_differentiable(out[1])
         return out[0], out[1]
 
     @staticmethod
     def backward(ctx, g_loss, _g_items):
-        # kernel wrote d(loss)/dp for grad_scale = 1; chain the upstream scalar (GradScaler's factor, WORLD_SIZE, ...)
-        if ctx.grads is None:
-            return (None, None) + (None,) * ctx.n
-        s = g_loss.reshape(())
-        return (None, None) + tuple(g * s.to(g.dtype) for g in ctx.grads)
+        p = ctx.saved_tensors
+        if not any(ctx.needs_input_grad[2:]):
+            return (None, None) + (None,) * len(p)
+        scale = g_loss.detach().reshape(-1)[:1].to(p[0].device, torch.float32).contiguous()
+        _, grads = ctx.crit._run(p, ctx.targets, want_grad=True, grad_scale=scale)
+        return (None, None) + tuple(grads)
 
 
 class ComputeLoss:
@@ -70,7 +77,7 @@ class ComputeLoss:
         q.grad_scale = 1.0
         return q
 
-    def _run(self, p, targets, want_grad):
+    def _run(self, p, targets, want_grad, grad_scale=None):
         if not all(t.is_cuda for t in p):
             raise RuntimeError("y5b200: ComputeLoss runs on CUDA tensors only (no CPU / PyTorch fallback)")
         lib = _lib.lib()
@@ -81,16 +88,22 @@ class ComputeLoss:
         need = int(lib.y5_loss_workspace_bytes(C.byref(q)))
         if need < 0:
             _lib.check(-1, "loss_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != dev:
-            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
-        ws_ptr = (self._ws.data_ptr() + 255) & ~255
+        key = (dev.index, _lib.stream_ptr(dev))  # scratch per (device, stream): concurrent streams never share it
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need + 256:
+            ws = self._ws[key] = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
         anchors = self.anchors.to(dev, torch.float32).contiguous()
         out = torch.empty(4, dtype=torch.float32, device=dev)
         grads = [torch.empty_like(t) for t in p] if want_grad else None
         pl = (C.c_void_p * self.nl)(*[t.data_ptr() for t in p])
         gl = (C.c_void_p * self.nl)(*[g.data_ptr() for g in grads]) if want_grad else None
-        _lib.check(lib.y5_loss_fwd_bwd(C.byref(q), pl, tg.data_ptr(), anchors.data_ptr(), out.data_ptr(), gl, ws_ptr, need,
-                                       C.c_void_p(_lib.stream_ptr(dev))), "loss_fwd_bwd")
+        with _lib.on(dev):
+            _lib.check(lib.y5_loss_fwd_bwd_scaled(C.byref(q), pl, tg.data_ptr(), anchors.data_ptr(), out.data_ptr(), gl,
+                                                  grad_scale.data_ptr() if grad_scale is not None else None, ws_ptr, need,
+                                                  C.c_void_p(_lib.stream_ptr(dev))), "loss_fwd_bwd")
         self._last = (q, ws_ptr)
         return (out[0:1], out[1:4]), grads
 
