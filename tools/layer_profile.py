@@ -23,9 +23,9 @@ meta = {}
 _orig = engine.Program.conv
 
 
-def conv(self, x, out, w, b, k, s, p, act, residual=None, name="conv", virt=None):
+def conv(self, x, out, w, b, k, s, p, act, residual=None, name="conv", virt=None, packed=None):
     n0 = len(self.ops)
-    _orig(self, x, out, w, b, k, s, p, act, residual, name, virt)
+    _orig(self, x, out, w, b, k, s, p, act, residual, name, virt, packed)
     m = self.B * out.h * out.w
     if virt is None:
         cin, kk, in_el = x.c, k * k, self.B * x.h * x.w * x.c
@@ -63,6 +63,26 @@ for i, op in enumerate(prog.ops):
         print(f"{md['name']:28s} {md['M']:8d} {md['N']:5d} {md['K']:5d} {us:8.1f} {md['bytes'] / us / 1e3:7.0f} {md['flops'] / us / 1e6:6.1f}  {md['bytes'] / 6569e3:8.1f}")
     else:
         print(f"{op.name:28s} {'':8s} {'':5s} {'':5s} {acc[i] * 1e3:8.1f}")
+# Detect-head GEMMs (they run outside the captured graph: fresh output tensors per call)
+no = prog.det_shapes[0][-1]
+zbuf = torch.empty(prog.B, prog.z_rows, no, dtype=prog.dtype, device=dev)
+raws = [torch.empty(sh, dtype=prog.dtype, device=dev) for sh in prog.det_shapes]
+hev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prog.head_ops]
+hacc = [0.0] * len(prog.head_ops)
+for _ in range(reps):
+    torch.cuda._sleep(40_000_000)
+    for plan, raw, (s, e) in zip(prog.head_ops, raws, hev):
+        s.record()
+        _lib.check(prog.lib.y5_detect_plan_run_to(plan, raw.data_ptr(), zbuf.data_ptr(), C.c_void_p(st)), "detect")
+        e.record()
+    torch.cuda.synchronize()
+    for i, (s, e) in enumerate(hev):
+        hacc[i] += s.elapsed_time(e) / reps
+for i, sh in enumerate(prog.det_shapes):
+    mrows = sh[0] * sh[2] * sh[3]
+    byt = 2 * (mrows * prog.outs[[17, 20, 23][i]].c + 2 * mrows * sh[1] * sh[4]) if len(prog.outs) > 23 else 0
+    print(f"{'detect.' + str(i):28s} {mrows:8d} {sh[1] * sh[4]:5d} {'':5s} {hacc[i] * 1e3:8.1f} {byt / max(hacc[i], 1e-9) / 1e6:7.0f} {'':6s}  {byt / 6569e3:8.1f}")
+print(f"fixed ops + head {tot + sum(hacc):.3f} ms")
 # head + stem timing
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()

@@ -65,6 +65,7 @@ struct ConvParams {
     int Ho, Wo, HoWo, stride, pad_h, pad_w;
     int tw, th, tiles_x, tiles_y;  // PATCH: spatial sub-tile th x tw (= 128 pixels), sub-tiles per image
     int a_stages, b_stages;
+    int b_resident;             // weights of the (single) N tile stay in shared memory for the whole kernel: loaded with the first tile only
     uint32_t a_sub_bytes, a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
     int is_bf16, act;
@@ -107,6 +108,63 @@ __host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, i
     o += 16;
     L.total = o;
     return L;
+}
+
+// Detect-head epilogue for one 32-column chunk of a row: logits -> raw + decoded (models/yolo.py:103-109), both written into the
+// shared-memory staging blocks that mirror the global [pixel][no] layout.  Values are packed in pairs and stored as 32-bit
+// words: a row starts on an odd 16-bit element when row*no is odd (no = 85), so the pairing shifts by one for those rows and
+// the two boundary elements go out as 16-bit stores (the neighbouring halves of those words belong to other threads).
+template <int C>
+__device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int no, int nc, float fgx, float fgy,
+                                           float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
+                                           uint16_t* __restrict__ stage_z, int row) {
+    uint16_t hr[32], hz[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        constexpr int base = C * 32;
+        const int o = base + j;
+        const float x = __uint_as_float(v[j]) + bias[o];
+        float d = x;
+        if (o < 5 + nc) {
+            const float sg = sigmoid_f(x);
+            if (C == 0 && j == 0) d = (sg * 2.0f + fgx) * det_stride;
+            else if (C == 0 && j == 1) d = (sg * 2.0f + fgy) * det_stride;
+            else if (C == 0 && j == 2) { const float t = sg * 2.0f; d = t * t * aw; }
+            else if (C == 0 && j == 3) { const float t = sg * 2.0f; d = t * t * ah; }
+            else d = sg;
+        }
+        hr[j] = pack1(x, bf16);
+        hz[j] = pack1(d, bf16);
+    }
+    const int e0 = row * no + C * 32;     // first element of this thread's chunk inside the [128][no] block
+    const int n_here = min(32, no - C * 32);
+    const int odd = e0 & 1;
+    uint16_t* pr = stage_raw + e0;
+    uint16_t* pz = stage_z + e0;
+    if (!odd) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (2 * j + 1 < n_here) {
+                *reinterpret_cast<uint32_t*>(pr + 2 * j) = static_cast<uint32_t>(hr[2 * j]) | (static_cast<uint32_t>(hr[2 * j + 1]) << 16);
+                *reinterpret_cast<uint32_t*>(pz + 2 * j) = static_cast<uint32_t>(hz[2 * j]) | (static_cast<uint32_t>(hz[2 * j + 1]) << 16);
+            } else if (2 * j < n_here) {
+                pr[2 * j] = hr[2 * j];
+                pz[2 * j] = hz[2 * j];
+            }
+        }
+    } else {
+        if (n_here > 0) { pr[0] = hr[0]; pz[0] = hz[0]; }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (2 * j + 2 < n_here) {
+                *reinterpret_cast<uint32_t*>(pr + 2 * j + 1) = static_cast<uint32_t>(hr[2 * j + 1]) | (static_cast<uint32_t>(hr[2 * j + 2]) << 16);
+                *reinterpret_cast<uint32_t*>(pz + 2 * j + 1) = static_cast<uint32_t>(hz[2 * j + 1]) | (static_cast<uint32_t>(hz[2 * j + 2]) << 16);
+            } else if (2 * j + 1 < n_here) {
+                pr[2 * j + 1] = hr[2 * j + 1];
+                pz[2 * j + 1] = hz[2 * j + 1];
+            }
+        }
+    }
 }
 
 template <int BLOCK_N, int EPI, int MT>
@@ -230,6 +288,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < grp; ++j) {
                         const int r = patch ? j : r0;
                         const int kb = (r * p.kw + s) * p.c_chunks + cc;
+                        if (p.b_resident) {  // slot kb holds k-block kb for every tile of this CTA (single N tile)
+                            if (tile == tile0 && elect_one()) {
+                                mbar_arrive_expect_tx(&b_full[kb], p.b_stage_bytes);
+                                tma_load_2d(&tmB, &b_full[kb], sB + kb * p.b_stage_bytes, kb * p.block_k, n0);
+                            }
+                            __syncwarp();
+                            continue;
+                        }
                         mbar_wait(&b_empty[bs], bph ^ 1);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
@@ -275,7 +341,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&a_full[as], aph);
                     uint32_t a_lo = a_base + as * a_stage16;
                     for (int j = 0; j < grp; ++j) {
-                        mbar_wait(&b_full[bs], bph);
+                        if (p.b_resident) {
+                            bs = g;  // non-patch: group index == k-block index
+                            if (tile == tile0) mbar_wait(&b_full[bs], 0);
+                        } else {
+                            mbar_wait(&b_full[bs], bph);
+                        }
                         tc_fence_after();
                         const uint32_t b_lo = b_base + bs * b_stage16;
                         if (elect_one()) {
@@ -288,14 +359,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                          (accum | k) != 0 ? 1u : 0u);
                                 }
                             }
-                            if (csize == 1) umma_commit(&b_empty[bs]);
+                            if (p.b_resident) {}
+                            else if (csize == 1) umma_commit(&b_empty[bs]);
                             else umma_commit_mcast(&b_empty[bs], cmask);
                             if (j == grp - 1) umma_commit(&a_empty[as]);
                             if (j == grp - 1 && g == num_groups - 1) umma_commit(&tmem_full[acc]);
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        if (!p.b_resident && ++bs == p.b_stages) { bs = 0; bph ^= 1; }
                         a_lo += a_shift16;
                     }
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
@@ -411,27 +483,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 if (slot * 32 < no) {
-                    const int c = slot;
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + c * 32, v);
+                    tmem_ld_32x32(t_row + slot * 32, v);
                     tmem_ld_wait();
                     const float fgx = static_cast<float>(gx) - 0.5f, fgy = static_cast<float>(gy) - 0.5f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int o = c * 32 + j;
-                        if (o < no) {
-                            const float x = __uint_as_float(v[j]) + sBias[n0 + o];
-                            float d = x;
-                            if (o < 5 + p.nc) {
-                                const float sg = sigmoid_f(x);
-                                if (o == 0) d = (sg * 2.0f + fgx) * p.det_stride;
-                                else if (o == 1) d = (sg * 2.0f + fgy) * p.det_stride;
-                                else if (o < 4) { const float t = sg * 2.0f; d = t * t * p.anchor_wh[a * 2 + (o - 2)]; }
-                                else d = sg;
-                            }
-                            stage_raw[row * no + o] = pack1(x, bf16);
-                            stage_z[row * no + o] = pack1(d, bf16);
-                        }
+                    // column chunk as a compile-time constant: the xy / wh special cases exist only in chunk 0's code
+                    switch (slot) {
+                        case 0: head_chunk<0>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, p.anchor_wh[a * 2], p.anchor_wh[a * 2 + 1], bf16,
+                                              stage_raw, stage_z, row); break;
+                        case 1: head_chunk<1>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
+                        case 2: head_chunk<2>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
+                        default: head_chunk<3>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
                     }
                 }
                 tc_fence_before();
@@ -613,10 +675,25 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1) {
     const bool patch = p.a_mode == A_PATCH;
     const int num_kb = p.kh * p.kw * p.c_chunks;
     int a_st = 0, b_st = 0;
-    if (!patch) {
+    // tuning knobs (A/B runs): Y5_STAGE_CAP=1 restores the round-1 rule "no more stages than k-blocks + 1";
+    // Y5_B_RESIDENT=0 turns the resident-weights mode off
+    static const bool stage_cap = [] { const char* e = getenv("Y5_STAGE_CAP"); return e && e[0] == '1'; }();
+    static const bool allow_resident = [] { const char* e = getenv("Y5_B_RESIDENT"); return !(e && e[0] == '0'); }();
+    p.b_resident = 0;
+    if (!patch && allow_resident && cluster == 1 && p.num_n_tiles == 1 && num_kb <= kMaxStages &&
+        static_cast<uint32_t>(num_kb) * p.b_stage_bytes <= 132u * 1024u) {
+        // one N tile: every tile of the CTA multiplies by the same weights -> keep all of its k-blocks in shared memory (loaded
+        // once) and give the rest of the budget to the activation ring.  Cuts the L2 -> smem traffic of small-K layers by the
+        // weight share (half of it for a 128x128x128 1x1 conv) and deepens the activation prefetch.
+        for (int s = kMaxStages; s >= 2; --s)
+            if (smem_layout(epi, p.no, p.bias_n, s, num_kb, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = s; break; }
+        if (a_st >= 2) { b_st = num_kb < 2 ? 2 : num_kb; p.b_resident = 1; }
+    }
+    if (p.b_resident) {
+    } else if (!patch) {
         for (int s = kMaxStages; s >= 2; --s)
             if (smem_layout(epi, p.no, p.bias_n, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
-        if (a_st > num_kb + 1) a_st = b_st = (num_kb + 1 < 2 ? 2 : num_kb + 1);
+        if (stage_cap && a_st > num_kb + 1) a_st = b_st = (num_kb + 1 < 2 ? 2 : num_kb + 1);
     } else {
         for (int a = 3; a >= 2 && !a_st; --a)
             for (int b = kMaxStages; b >= 3; --b)
