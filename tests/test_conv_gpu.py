@@ -30,11 +30,16 @@ CASES = [
 def test_conv_vs_oracle(cuda, dtype, case):
     got, ref, _ = conv_case(cuda, dtype, *case)
     assert rel_err(got, ref) < TOL[dtype], (case, rel_err(got, ref))
+    got, ref, _ = conv_case(cuda, dtype, *case, direct_store=True)
+    assert rel_err(got, ref) < TOL[dtype], (case, "direct stores", rel_err(got, ref))
 
 
-@pytest.mark.parametrize("case", [(2, 20, 20, 64, 64, 3, 1, 1), (2, 16, 16, 64, 128, 1, 1, 0)])
-def test_conv_residual_and_slices(cuda, case):
-    got, ref, untouched = conv_case(cuda, torch.float16, *case, residual=True, in_extra=24, out_extra=40)
+@pytest.mark.parametrize("direct_store", [False, True])
+@pytest.mark.parametrize("case", [(2, 20, 20, 64, 64, 3, 1, 1), (2, 16, 16, 64, 128, 1, 1, 0), (5, 7, 9, 64, 40, 1, 1, 0), (3, 13, 27, 32, 72, 3, 1, 1)])
+def test_conv_residual_and_slices(cuda, case, direct_store):
+    """Both epilogue store paths (per-warp staging + cp.async.bulk.tensor store, and the direct row-strided stores) into a
+    channel slice of a wider buffer: N tails inside a 32-channel chunk (40, 72 channels), partial spatial tiles, M tails."""
+    got, ref, untouched = conv_case(cuda, torch.float16, *case, residual=True, in_extra=24, out_extra=40, direct_store=direct_store)
     assert rel_err(got, ref) < 2e-3
     assert untouched, "epilogue wrote outside its channel slice"
 
@@ -78,6 +83,27 @@ def test_conv_cluster_multicast(cuda, bn, mt2, case, a_mode):
     counts leave one CTA of the last cluster without work (it must still take part in the multicast protocol)."""
     got, ref, _ = conv_case(cuda, torch.float16, *case, block_n=bn, mt2=mt2, cluster=2, a_mode=a_mode, residual=True)
     assert rel_err(got, ref) < 2e-3, (bn, mt2, case, a_mode, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bn,mt2", [(128, False), (128, True), (256, False)])
+@pytest.mark.parametrize("case,a_mode", [((4, 40, 40, 64, 256, 3, 1, 1), 2), ((4, 40, 40, 64, 256, 3, 1, 1), 1), ((5, 24, 24, 128, 512, 1, 1, 0), 0),
+                                         ((3, 40, 40, 128, 384, 3, 2, 1), 0), ((2, 80, 80, 128, 128, 3, 1, 1), 2), ((1, 20, 20, 512, 512, 3, 1, 1), 0)])
+def test_conv_cta_pairs(cuda, dtype, bn, mt2, case, a_mode):
+    """cta_group::2: the two CTAs of a cluster run ONE M = 256 MMA per k-step, each staging its own 128 activation rows and half
+    of the weight tile; full barriers in the leader collect both CTAs' TMA bytes, the follower's epilogue releases the leader's
+    accumulator barrier remotely.  Odd super-tile counts (the follower of the last pair has no rows), N tails (384 = 1.5 tiles of
+    256), every fetch mode, residual operand."""
+    if case[4] % bn and bn == 256 and case[4] < 256:
+        pytest.skip("N tile wider than the layer")
+    got, ref, _ = conv_case(cuda, dtype, *case, block_n=bn, mt2=mt2, cg2=True, a_mode=a_mode, residual=True)
+    assert rel_err(got, ref) < TOL[dtype], (bn, mt2, case, a_mode, rel_err(got, ref))
+
+
+def test_conv_cta_pairs_many_tiles(cuda):
+    """Every pair loops over several tiles (barrier phase wrap-around across the pair protocol)."""
+    got, ref, _ = conv_case(cuda, torch.float16, 16, 80, 80, 64, 256, 3, 1, 1, block_n=256, cg2=True)  # 800 M tiles -> 400 pair tiles
+    assert rel_err(got, ref) < 2e-3
 
 
 def test_tensor_core_path_agrees_with_direct_kernel(cuda):

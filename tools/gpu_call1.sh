@@ -2,7 +2,7 @@
 set +e
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -x --deselect tests/test_train_ddp_gpu.py 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 --deselect tests/test_train_ddp_gpu.py 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3 > gpurun_out/smoke.log; cat gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -3 gpurun_out/bench_default.err

@@ -87,6 +87,13 @@ def model_cfg(name: str) -> dict:
 # reference data/hyps/hyp.scratch-low.yaml -- only the keys the loss path reads
 # (utils/loss.py:107-132 and train.py:326-328).
 HYP_SCRATCH_LOW = {
+    "lr0": 0.01,
+    "lrf": 0.01,
+    "momentum": 0.937,
+    "weight_decay": 0.0005,
+    "warmup_epochs": 3.0,
+    "warmup_momentum": 0.8,
+    "warmup_bias_lr": 0.1,
     "box": 0.05,
     "cls": 0.5,
     "cls_pw": 1.0,

@@ -108,6 +108,39 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the copy lands in THIS CTA's shared memory but signals the mbarrier at `bar_addr`, a
+// shared::cluster address that may belong to the pair's leader CTA (one barrier then collects the bytes of both CTAs' copies)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_cg2(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c, int w, int h, int n,
+                                                       uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) as seen in CTA `rank` of the cluster (same offset)
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {  // arrive (count 1) on a barrier anywhere in the cluster
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
@@ -135,6 +168,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// CTA-pair allocation: executed by the same warp index of BOTH CTAs of the pair; each CTA gets the same column range
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -151,13 +192,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
     return d;
 }
 // kind::f16 instruction descriptor: D fp32, A/B fp16 or bf16, both K-major, M=128.
-__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(bool bf16, uint32_t n) {
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(bool bf16, uint32_t n, uint32_t m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                   // D format: F32
     d |= (bf16 ? 1u : 0u) << 7;     // A format
     d |= (bf16 ? 1u : 0u) << 10;    // B format
     d |= (n >> 3) << 17;            // N / 8
-    d |= (128u >> 4) << 24;         // M / 16
+    d |= (m >> 4) << 24;            // M / 16  (128 for one CTA, 256 for a CTA pair: 128 rows in each CTA's TMEM)
     return d;
 }
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -186,6 +227,26 @@ __device__ __forceinline__ void umma_f16_ss_lohi(uint32_t tmem_d, uint32_t a_lo,
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
         : "memory");
+}
+// CTA-pair MMA (issued by the leader CTA only): M = 256 = this CTA's 128 rows + the peer's, A read from both CTAs' shared memory
+// at the same offset, B = the two CTAs' N/2-row halves, D in both CTAs' TMEM at the same address
+__device__ __forceinline__ void umma_f16_ss_lohi_cg2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                     uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// pair commit: arrives on the barrier at this offset in every CTA of `mask` once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 // arrives (count 1) on `bar` once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

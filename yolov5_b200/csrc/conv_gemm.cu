@@ -65,6 +65,8 @@ struct ConvParams {
     int Ho, Wo, HoWo, stride, pad_h, pad_w;
     int tw, th, tiles_x, tiles_y;  // PATCH: spatial sub-tile th x tw (= 128 pixels), sub-tiles per image
     int a_stages, b_stages;
+    int tma_store;              // epilogue: per-warp swizzled smem staging + cp.async.bulk.tensor store instead of row-strided STG
+    int c_bw, c_bh;             // PATCH + tma_store: store box = c_bw pixels x c_bh rows (c_bw * c_bh = 32)
     int b_resident;             // weights of the (single) N tile stay in shared memory for the whole kernel: loaded with the first tile only
     uint32_t a_sub_bytes, a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
@@ -99,6 +101,7 @@ __host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, i
     o = (o + 1023) & ~1023u;
     L.off_out = o;
     if (epi == 1) o += 4 * ((kBlockM * no * 2 + 1023) & ~1023u);  // head: 2 sets x {raw, decoded} blocks [128][no], global layout
+    if (epi == 2) o += kEpiWarps * 2048;                           // EPI 0 with TMA store: one [32 rows][32 ch] staging tile per epilogue warp
     L.off_bias = o;
     o += ((bias_n + 3) & ~3) * 4;
     o = (o + 7) & ~7u;
@@ -167,9 +170,18 @@ __device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float*
     }
 }
 
-template <int BLOCK_N, int EPI, int MT>
+// CG = 2: CTA-pair mode (tcgen05 cta_group::2).  The two CTAs of a cluster work on two M super-tiles of the SAME N tile as ONE
+// M = 256 MMA: each CTA stages its own 128 activation rows and HALF of the weight tile (BLOCK_N / 2 rows), the leader's MMA
+// reads both CTAs' shared memory and writes 128 x BLOCK_N accumulators into each CTA's TMEM.  Weight traffic L2 -> smem per
+// CTA halves (it is the larger operand of the 3x3 layers), which is what bounds them with cta_group::1.  Barrier protocol:
+// "full" barriers live in the leader only and collect the transaction bytes of BOTH CTAs' TMA copies (cp.async.bulk.tensor
+// .cta_group::2 may signal the peer's barrier); "empty" / "accumulator full" arrive in both CTAs through the multicast form of
+// tcgen05.commit; the follower's epilogue warps arrive remotely on the leader's "accumulator empty" barrier.
+template <int BLOCK_N, int EPI, int MT, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const ConvParams p) {
+    static_assert(CG == 1 || (EPI == 0 && BLOCK_N >= 128), "CTA pairs: plain epilogue, N tile >= 128");
     constexpr int kAccCols = MT * BLOCK_N;          // TMEM columns per accumulator set (128, 256 or 512)
     constexpr int NACC = kAccCols <= 256 ? 2 : 1;   // two sets when they fit: epilogue of tile i overlaps the MMAs of tile i+1
     constexpr uint32_t kTmemCols = NACC * kAccCols < 32 ? 32 : NACC * kAccCols;
@@ -178,7 +190,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const SmemLayout L = smem_layout(EPI, p.no, p.bias_n, p.a_stages, p.b_stages, p.a_stage_bytes, p.b_stage_bytes);
+    const SmemLayout L = smem_layout(EPI == 1 ? 1 : (p.tma_store ? 2 : 0), p.no, p.bias_n, p.a_stages, p.b_stages, p.a_stage_bytes, p.b_stage_bytes);
     uint8_t* sA = smem + L.off_a;
     uint8_t* sB = smem + L.off_b;
     float* sBias = reinterpret_cast<float*>(smem + L.off_bias);
@@ -201,19 +213,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (EPI == 0 && p.tma_store) tma_prefetch_desc(&tmC);
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], csize);  // released by the MMA thread of every CTA in the cluster
+            mbar_init(&b_empty[s], CG == 2 ? 1 : csize);  // multicast mode: released by the MMA thread of every CTA in the cluster
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], kEpiWarps);
+            mbar_init(&tmem_empty[s], CG * kEpiWarps);  // pair mode: the epilogue warps of both CTAs release the leader's barrier
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp == 1) { if (CG == 2) tmem_alloc_cg2(tmem_ptr_smem, kTmemCols); else tmem_alloc(tmem_ptr_smem, kTmemCols); }
     if (warp >= 2)  // whole folded-BN bias vector once: no per-tile global loads on the epilogue's critical path
         for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) sBias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
     tc_fence_before();
@@ -272,11 +285,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 auto issue_group = [&](int cc, int s, int r0) {
                     mbar_wait(&a_empty[as], aph ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&a_full[as], p.a_stage_bytes);
+                        if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&a_full[as], CG * p.a_stage_bytes);  // pair: both CTAs' bytes
+                        const uint32_t a_bar = CG == 2 ? mapa_u32(&a_full[as], 0) : 0;                      // the leader's barrier
 #pragma unroll
                         for (int mi = 0; mi < MT; ++mi) {
                             uint8_t* a_dst = sA + as * p.a_stage_bytes + mi * p.a_sub_bytes;
-                            if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
+                            if (CG == 2) {
+                                if (p.a_mode == A_LINEAR) tma_load_2d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
+                                else if (p.a_mode == A_IM2COL)
+                                    tma_load_im2col_4d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
+                                                           static_cast<uint16_t>(s), static_cast<uint16_t>(r0));
+                                else tma_load_4d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, x0[mi] + s, y0[mi], img[mi]);
+                            } else if (p.a_mode == A_LINEAR) tma_load_2d(&tmA, &a_full[as], a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
                             else if (p.a_mode == A_IM2COL)
                                 tma_load_im2col_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
                                                    static_cast<uint16_t>(s), static_cast<uint16_t>(r0));
@@ -298,8 +318,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         mbar_wait(&b_empty[bs], bph ^ 1);
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(&b_full[bs], p.b_stage_bytes);
-                            if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
+                            if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&b_full[bs], CG * p.b_stage_bytes);
+                            if (CG == 2)  // my half of the weight tile's rows, into my own shared memory; bytes counted by the leader
+                                tma_load_2d_cg2(&tmB, mapa_u32(&b_full[bs], 0), sB + bs * p.b_stage_bytes, kb * p.block_k,
+                                                n0 + static_cast<int>(crank) * (BLOCK_N / 2));
+                            else if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
                             else {  // my slice of the rows, delivered to every CTA of the cluster
                                 const uint32_t slice_rows = BLOCK_N / csize;
                                 tma_load_2d_mcast(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes + crank * slice_rows * row_bytes,
@@ -322,7 +345,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        {   // whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
+        if (CG == 1 || crank == 0) {   // pair mode: the leader CTA issues for both.  whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase = 0;
             const int k_steps = p.block_k / 16;
@@ -354,16 +377,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int k = 0; k < 4; ++k) {
                                 if (k < k_steps) {
 #pragma unroll
-                                    for (int mi = 0; mi < MT; ++mi)
-                                        umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
-                                                         (accum | k) != 0 ? 1u : 0u);
+                                    for (int mi = 0; mi < MT; ++mi) {
+                                        if (CG == 2)
+                                            umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
+                                                                 (accum | k) != 0 ? 1u : 0u);
+                                        else
+                                            umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
+                                                             (accum | k) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
-                            if (p.b_resident) {}
-                            else if (csize == 1) umma_commit(&b_empty[bs]);
-                            else umma_commit_mcast(&b_empty[bs], cmask);
-                            if (j == grp - 1) umma_commit(&a_empty[as]);
-                            if (j == grp - 1 && g == num_groups - 1) umma_commit(&tmem_full[acc]);
+                            if (CG == 2) {  // every release / publication reaches both CTAs of the pair
+                                umma_commit_cg2(&b_empty[bs], 3);
+                                if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
+                                if (j == grp - 1 && g == num_groups - 1) umma_commit_cg2(&tmem_full[acc], 3);
+                            } else {
+                                if (p.b_resident) {}
+                                else if (csize == 1) umma_commit(&b_empty[bs]);
+                                else umma_commit_mcast(&b_empty[bs], cmask);
+                                if (j == grp - 1) umma_commit(&a_empty[as]);
+                                if (j == grp - 1 && g == num_groups - 1) umma_commit(&tmem_full[acc]);
+                            }
                         }
                         __syncwarp();
                         accum = 1;
@@ -432,6 +466,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld_32x32(t_row + c * 32, v);
                     tmem_ld_wait();
                     uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (gpix * p.out_pitch + n0 + col) * 2;
+                    const bool staged = p.tma_store != 0;
+                    uint8_t* stg = smem + L.off_out + ew * 2048;  // this warp's [32 rows][32 channels] tile, 64-byte rows, SWIZZLE_64B
+                    if (staged) {  // the previous bulk store of this warp must have finished READING the staging tile
+                        if (lane == 0) tma_store_wait_read0();
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         float f[8];
@@ -449,19 +489,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 f[2 * j + 1] += t.y;
                             }
                         }
-                        if (live && n0 + col + g * 8 < p.N) {
-                            uint4 o;
-                            o.x = pack2(f[0], f[1], bf16);
-                            o.y = pack2(f[2], f[3], bf16);
-                            o.z = pack2(f[4], f[5], bf16);
-                            o.w = pack2(f[6], f[7], bf16);
-                            *reinterpret_cast<uint4*>(op + g * 16) = o;
+                        uint4 o;
+                        o.x = pack2(f[0], f[1], bf16);
+                        o.y = pack2(f[2], f[3], bf16);
+                        o.z = pack2(f[4], f[5], bf16);
+                        o.w = pack2(f[6], f[7], bf16);
+                        if (staged) *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+                        else if (live && n0 + col + g * 8 < p.N) *reinterpret_cast<uint4*>(op + g * 16) = o;
+                    }
+                    if (staged) {
+                        // one bulk tensor store per (warp, chunk): the copy engine writes whole 64-byte row segments and clips
+                        // rows / pixels / channels beyond the tensor, so no per-thread masks are needed
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && mt < p.num_m_tiles && n0 + col < p.N) {
+                            if (patch) {
+                                const int img = mt / per_img;
+                                const int rem = mt - img * per_img;
+                                const int tyi = rem / p.tiles_x;
+                                const int pos0 = quarter * 32;
+                                const int y_in = pos0 >> tw_shift, x_in = pos0 & ((1 << tw_shift) - 1);
+                                tma_store_4d(&tmC, stg, n0 + col, (rem - tyi * p.tiles_x) * p.tw + x_in, tyi * p.th + y_in, img);
+                            } else {
+                                tma_store_2d(&tmC, stg, n0 + col, mt * kBlockM + quarter * 32);
+                            }
+                            tma_store_commit();
                         }
                     }
                 }
+                if (p.tma_store && lane == 0) tma_store_wait_read0();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // this warp is done with the accumulator set
+                if (lane == 0) {  // this warp is done with the accumulator set (pair mode: tell the leader, it issues the MMAs)
+                    if (CG == 2 && crank != 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+                    else mbar_arrive(&tmem_empty[acc]);
+                }
             } else {
                 // ---- Detect head (models/yolo.py:95-113): N tile `nt` == anchor.  One TMEM pass produces the raw logits AND
                 // the decoded predictions into two smem blocks laid out exactly like their global destinations
@@ -526,12 +588,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
 
+    if (EPI == 0 && p.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();  // bulk stores issued by this thread are complete
     tc_fence_before();
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -625,9 +689,9 @@ void pick_tile(int out_c, int a_mode, int k_total, int64_t m_tiles, int* block_n
     // (going further down to 128-wide tiles was measured slower on yolov5s' 20x20 layers: 1.98 vs 1.83 ms per forward)
 }
 
-template <int BN, int EPI, int MT>
-cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, int grid, int cluster, uint32_t smem, cudaStream_t st) {
-    const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_kernel<BN, EPI, MT>), 227 * 1024);
+template <int BN, int EPI, int MT, int CG = 1>
+cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const ConvParams& p, int grid, int cluster, uint32_t smem, cudaStream_t st) {
+    const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_kernel<BN, EPI, MT, CG>), 227 * 1024);
     if (attr_err != cudaSuccess) return attr_err;
     count_launch();
     static const bool pdl = [] { const char* e = getenv("Y5_PDL"); return !(e && e[0] == '0'); }();
@@ -652,33 +716,36 @@ cudaError_t launch_conv(const CUtensorMap& a, const CUtensorMap& b, const ConvPa
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, MT>, a, b, p);
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, MT, CG>, a, b, c, p);
 }
 
 struct PlanCommon {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     ConvParams p;
     int block_n, epi, mt, grid, cluster;
+    int cg;  // 2 = CTA-pair MMA (cta_group::2): cluster == 2, each CTA stages half of every weight tile
     uint32_t smem_bytes;
 };
 
 // stage counts from the shared-memory budget; fills p.a_stages/b_stages and pc.smem_bytes/grid.
 // Expects p.a_sub_bytes, p.b_stage_bytes, p.num_m_tiles set.
-int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1) {
+int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1, int cg = 1) {
     ConvParams& p = pc.p;
+    pc.cg = cg;
     p.a_stage_bytes = mt * p.a_sub_bytes;
     p.num_m_super = (p.num_m_tiles + mt - 1) / mt;
     p.num_n_tiles = epi == 1 ? p.na : (p.N + block_n - 1) / block_n;
     p.bias_n = p.num_n_tiles * block_n;
-    p.idesc = umma_idesc_f16(p.is_bf16 != 0, block_n);
+    p.idesc = umma_idesc_f16(p.is_bf16 != 0, block_n, cg == 2 ? 256 : 128);
     const uint32_t budget = 225 * 1024 - 1024;
     const bool patch = p.a_mode == A_PATCH;
+    const int lay = epi == 1 ? 1 : (p.tma_store ? 2 : 0);  // shared-memory layout variant (see smem_layout)
     const int num_kb = p.kh * p.kw * p.c_chunks;
     int a_st = 0, b_st = 0;
     // tuning knobs (A/B runs): Y5_STAGE_CAP=1 restores the round-1 rule "no more stages than k-blocks + 1";
-    // Y5_B_RESIDENT=0 turns the resident-weights mode off
+    // Y5_B_RESIDENT=1 turns the resident-weights mode on (measured 5-15 % slower on the 1x1 layers of yolov5l: opt-in)
     static const bool stage_cap = [] { const char* e = getenv("Y5_STAGE_CAP"); return e && e[0] == '1'; }();
-    static const bool allow_resident = [] { const char* e = getenv("Y5_B_RESIDENT"); return !(e && e[0] == '0'); }();
+    static const bool allow_resident = [] { const char* e = getenv("Y5_B_RESIDENT"); return e && e[0] == '1'; }();  // measured slower: opt-in
     p.b_resident = 0;
     if (!patch && allow_resident && cluster == 1 && p.num_n_tiles == 1 && num_kb <= kMaxStages &&
         static_cast<uint32_t>(num_kb) * p.b_stage_bytes <= 132u * 1024u) {
@@ -686,24 +753,24 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1) {
         // once) and give the rest of the budget to the activation ring.  Cuts the L2 -> smem traffic of small-K layers by the
         // weight share (half of it for a 128x128x128 1x1 conv) and deepens the activation prefetch.
         for (int s = kMaxStages; s >= 2; --s)
-            if (smem_layout(epi, p.no, p.bias_n, s, num_kb, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = s; break; }
+            if (smem_layout(lay, p.no, p.bias_n, s, num_kb, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = s; break; }
         if (a_st >= 2) { b_st = num_kb < 2 ? 2 : num_kb; p.b_resident = 1; }
     }
     if (p.b_resident) {
     } else if (!patch) {
         for (int s = kMaxStages; s >= 2; --s)
-            if (smem_layout(epi, p.no, p.bias_n, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
+            if (smem_layout(lay, p.no, p.bias_n, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
         if (stage_cap && a_st > num_kb + 1) a_st = b_st = (num_kb + 1 < 2 ? 2 : num_kb + 1);
     } else {
         for (int a = 3; a >= 2 && !a_st; --a)
             for (int b = kMaxStages; b >= 3; --b)
-                if (smem_layout(epi, p.no, p.bias_n, a, b, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = a; b_st = b; break; }
+                if (smem_layout(lay, p.no, p.bias_n, a, b, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = a; b_st = b; break; }
     }
     if (a_st < 2 || b_st < 2) return set_error(Y5_E_UNSUPPORTED, "conv tile does not fit shared memory (block_n %d a %u b %u)", block_n,
                                                 p.a_stage_bytes, p.b_stage_bytes);
     p.a_stages = a_st;
     p.b_stages = b_st;
-    pc.smem_bytes = smem_layout(epi, p.no, p.bias_n, a_st, b_st, p.a_stage_bytes, p.b_stage_bytes).total + 1024;
+    pc.smem_bytes = smem_layout(lay, p.no, p.bias_n, a_st, b_st, p.a_stage_bytes, p.b_stage_bytes).total + 1024;
     pc.block_n = block_n;
     pc.epi = epi;
     pc.mt = mt;
@@ -716,15 +783,18 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1) {
 
 int run_plan(const PlanCommon& pc, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
-    const int key = pc.epi * 10000 + pc.block_n * 10 + pc.mt;
+    const int key = (pc.cg == 2 ? 100000 : 0) + pc.epi * 10000 + pc.block_n * 10 + pc.mt;
     switch (key) {
-        case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 1282: e = launch_conv<128, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 2561: e = launch_conv<256, 0, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 2562: e = launch_conv<256, 0, 2>(pc.tmA, pc.tmB, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
-        case 11281: e = launch_conv<kHeadN, 1, 1>(pc.tmA, pc.tmB, pc.p, pc.grid, 1, pc.smem_bytes, st); break;
+        case 101281: e = launch_conv<128, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
+        case 101282: e = launch_conv<128, 0, 2, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
+        case 102561: e = launch_conv<256, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
+        case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 1282: e = launch_conv<128, 0, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 2561: e = launch_conv<256, 0, 1>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 2562: e = launch_conv<256, 0, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
+        case 11281: e = launch_conv<kHeadN, 1, 1>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 1, pc.smem_bytes, st); break;
         default: return set_error(Y5_E_UNSUPPORTED, "conv: no kernel for block_n %d mt %d epi %d", pc.block_n, pc.mt, pc.epi);
     }
     if (e != cudaSuccess) return set_error(int(e), "conv_gemm launch failed: %s", cudaGetErrorString(e));
@@ -814,7 +884,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     else if (d->a_mode == 2 || (d->a_mode == 0 && d->stride == 1 && best_eff >= 0.75)) a_mode_sel = A_PATCH;
     else a_mode_sel = A_IM2COL;
 
-    int bn = d->block_n, mt_sel = 0, cl_sel = 1;
+    int bn = d->block_n, mt_sel = 0, cl_sel = 1, cg_sel = 1;
     {
         int bn_auto = 0;
         pick_tile(d->out_c, a_mode_sel, g.kh * g.kw * d->in_c, (M64 + kBlockM - 1) / kBlockM, &bn_auto, &mt_sel, &cl_sel);
@@ -822,6 +892,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         else {  // forced block_n (tests / tuning): reserved bit 1 asks for MT = 2, bits 8.. give the cluster size
             mt_sel = bn < 128 ? 128 / bn : ((d->reserved & 2) ? 2 : 1);
             cl_sel = (d->reserved >> 8) > 1 ? (d->reserved >> 8) : 1;
+            if ((d->reserved & 4) && bn >= 128) { cg_sel = 2; cl_sel = 2; }  // CTA-pair MMA
         }
         if (const char* e = getenv("Y5_CLUSTER")) cl_sel = atoi(e) > 1 && bn >= 128 ? atoi(e) : 1;
         if (const char* e = getenv("Y5_BIG_TILE")) {  // tuning: "<block_n>x<mt>" for layers with out_c >= 256, e.g. 256x1
@@ -839,6 +910,21 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
             }
         }
         if (cl_sel != 1 && cl_sel != 2 && cl_sel != 4) cl_sel = 1;
+        // CTA-pair (cta_group::2) selection: Y5_CG2 = 0 off, 1 = layers with >= 256 output channels, 2 = also the 128-channel ones.
+        // A pair needs two M super-tiles per tile and enough pair-tiles to fill 74 pairs.
+        static const int cg2_mode = [] { const char* e = getenv("Y5_CG2"); return e ? atoi(e) : 0; }();
+        if (!d->block_n && cg2_mode > 0 && cg_sel == 1) {
+            const long long m_tiles = (M64 + kBlockM - 1) / kBlockM;
+            if (d->out_c >= 256 && d->out_c % 128 == 0) {
+                const int bn2 = d->out_c % 256 == 0 ? 256 : 128;
+                const long long pair_tiles = ((m_tiles + 1) / 2) * (d->out_c / bn2);
+                if (pair_tiles >= 60) { bn = bn2; mt_sel = 1; cg_sel = 2; cl_sel = 2; }
+            } else if (cg2_mode > 1 && d->out_c == 128) {
+                const int mt2 = a_mode_sel == A_LINEAR ? 1 : 2;
+                const long long pair_tiles = (m_tiles + 2 * mt2 - 1) / (2 * mt2);
+                if (pair_tiles >= 60) { bn = 128; mt_sel = mt2; cg_sel = 2; cl_sel = 2; }
+            }
+        }
     }
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
     auto* plan = new y5_conv_plan();
@@ -861,7 +947,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
     const int row_bytes = bk * 2;
-    p.b_stage_bytes = bn * row_bytes;
+    p.b_stage_bytes = bn / cg_sel * row_bytes;  // pair mode: each CTA stages half of the weight tile's rows
     p.a_mode = a_mode_sel;
 
     const CUtensorMapSwizzle sw = swizzle_for_row_bytes(row_bytes);
@@ -899,7 +985,30 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, dims, str, box, sw, "B");
     }
     if (e) { delete plan; return e; }
-    if (int e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel)) { delete plan; return e2; }
+    // epilogue store mode.  TMA store (per-warp staging + cp.async.bulk.tensor): a warp's 32 rows x 64 bytes leave as whole row
+    // segments instead of 4 x 32 row-strided 16-byte stores (128 L1 wavefronts per chunk), which is what bounds the memory-bound
+    // layers; costs 32 KB of the pipeline's shared memory.  Y5_TMA_STORE = 0 off, 1 on (default), reserved bit 4 (16) forces it off in tests.
+    static const int tma_store_mode = [] { const char* e = getenv("Y5_TMA_STORE"); return e ? atoi(e) : 1; }();
+    p.tma_store = (tma_store_mode != 0 && !(d->reserved & 16)) ? 1 : 0;
+    if (p.tma_store) {
+        int ce;
+        if (p.a_mode == A_PATCH) {
+            p.c_bw = p.tw < 32 ? p.tw : 32;
+            p.c_bh = 32 / p.c_bw;
+            cuuint64_t dims[4] = {(cuuint64_t)d->out_c, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)d->batch};
+            cuuint64_t str[3] = {(cuuint64_t)d->out_pitch * 2, (cuuint64_t)g.Wo * d->out_pitch * 2, (cuuint64_t)g.Ho * g.Wo * d->out_pitch * 2};
+            cuuint32_t box[4] = {32, (cuuint32_t)p.c_bw, (cuuint32_t)p.c_bh, 1};
+            ce = encode_tiled(&pc.tmC, d->dtype, d->out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, "C patch");
+        } else {
+            cuuint64_t dims[2] = {(cuuint64_t)d->out_c, (cuuint64_t)p.M};
+            cuuint64_t str[1] = {(cuuint64_t)d->out_pitch * 2};
+            cuuint32_t box[2] = {32, 32};
+            ce = encode_tiled(&pc.tmC, d->dtype, d->out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B, "C");
+        }
+        if (ce) p.tma_store = 0;  // a view the copy engine cannot describe: the direct-store epilogue handles everything
+    }
+    if (!p.tma_store) pc.tmC = pc.tmA;  // unused, but must be a valid descriptor for the launch
+    if (int e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel, cg_sel)) { delete plan; return e2; }
     *out = plan;
     return 0;
 }
@@ -984,6 +1093,7 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     cuuint32_t bbox[2] = {(cuuint32_t)bk, (cuuint32_t)kHeadN};
     e = encode_tiled(&pc.tmB, d->dtype, d->weight, 2, bdims, bstr, bbox, sw, "head B");
     if (e) { delete plan; return e; }
+    pc.tmC = pc.tmA;  // the head stages its outputs itself
     if (int e2 = finish_plan(pc, kHeadN, 1, 1)) { delete plan; return e2; }
     *out = plan;
     return 0;
