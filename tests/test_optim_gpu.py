@@ -167,11 +167,14 @@ def test_loss_gradient_under_gradscaler_scale(cuda, scale, dtype):
     for a, b in zip(p, pr):
         ga, gb = a.grad.float().cpu(), b.grad * scale
         assert bool(torch.isfinite(ga).all())
-        big = gb.abs() > 6e-5  # above fp16's subnormal range after scaling
-        assert float(((ga - gb).abs()[big] / gb.abs()[big]).max()) < 4 * eps
-        assert float((ga - gb).abs()[~big].max()) < 1e-4
-        obj = gb[..., 4]
-        assert float((ga[..., 4] != 0).float().mean()) > 0.99 and float(obj.abs().min()) > 0  # nothing flushed to zero
+        # whole tensor: box / class gradients of a cell are sums of several contributions accumulated in the prediction dtype (like
+        # autograd's index_put backward), so the bound is relative to the largest gradient, as in tests/test_loss_gpu.py
+        assert float((ga - gb).abs().max()) <= 4 * eps * float(gb.abs().max())
+        # objectness column: one writer per cell -> element-wise one rounding, INCLUDING the tiny gradients of confident negatives
+        # (2e-4 x sigmoid(-6): flushed to zero / subnormal if the scale were applied after rounding to fp16)
+        oa, ob = ga[..., 4], gb[..., 4]
+        assert float(((oa - ob).abs() / ob.abs()).max()) < 2 * eps
+        assert float(ob.abs().min()) > 0 and float((oa != 0).float().mean()) == 1.0
 
 
 def test_graphed_train_step_with_loss_scaling_ema_and_schedule(cuda):

@@ -39,9 +39,18 @@ pg = torch.autograd.grad(loss, p, retain_graph=True)
 p32r = [q.clone().requires_grad_(True) for q in p32]
 l2, _ = loss_ref.compute_loss([q.float().cpu() for q in p32r], targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)
 g2 = torch.autograd.grad(l2, p32r)
+pe = [q.detach().float().cpu().requires_grad_(True) for q in p]  # oracle loss evaluated AT THE ENGINE'S OWN MAPS: isolates the loss kernel
+l3, _ = loss_ref.compute_loss(pe, targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)
+g3 = torch.autograd.grad(l3, pe)
+pa = [q.detach().float().cpu().requires_grad_(True) for q in pamp]
+l4, _ = loss_ref.compute_loss(pa, targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)
+g4 = torch.autograd.grad(l4, pa)
 for l in range(3):
     a, r = pg[l].float().cpu(), g2[l].float().cpu()
-    print(f"dL/draw{l}: rel L2 {float((a - r).norm() / r.norm()):.3e}")
+    print(f"dL/draw{l}: kernel@engine-maps vs oracle@fp32-maps rel L2 {float((a - r).norm() / r.norm()):.3e} | kernel vs oracle@engine-maps "
+          f"{float((a - g3[l]).norm() / g3[l].norm()):.3e} | oracle@amp-maps vs oracle@fp32-maps {float((g4[l] - r).norm() / r.norm()):.3e} | "
+          f"mean signed raw err mine {float((p[l].detach().float().cpu() - p32[l].cpu()).mean()):.2e} amp {float((pamp[l].float().cpu() - p32[l].cpu()).mean()):.2e} "
+          f"| obj-col mean err mine {float((p[l].detach().float().cpu() - p32[l].cpu())[..., 4].mean()):.2e} amp {float((pamp[l].float().cpu() - p32[l].cpu())[..., 4].mean()):.2e}")
 loss.backward()
 named = dict(m.named_parameters())
 rows = []

@@ -121,50 +121,57 @@ template <int C>
 __device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int no, int nc, float fgx, float fgy,
                                            float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
                                            uint16_t* __restrict__ stage_z, int row) {
-    uint16_t hr[32], hz[32];
+    // words wr[j] / wz[j] = elements (2j, 2j+1) of this chunk, converted two at a time (cvt.rn.f16x2 / bf16x2)
+    uint32_t wr[16], wz[16];
+    const float4* b4 = reinterpret_cast<const float4*>(bias + C * 32);  // 128-byte aligned: bias vector base and C*32 floats
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        constexpr int base = C * 32;
-        const int o = base + j;
-        const float x = __uint_as_float(v[j]) + bias[o];
-        float d = x;
-        if (o < 5 + nc) {
-            const float sg = sigmoid_f(x);
-            if (C == 0 && j == 0) d = (sg * 2.0f + fgx) * det_stride;
-            else if (C == 0 && j == 1) d = (sg * 2.0f + fgy) * det_stride;
-            else if (C == 0 && j == 2) { const float t = sg * 2.0f; d = t * t * aw; }
-            else if (C == 0 && j == 3) { const float t = sg * 2.0f; d = t * t * ah; }
-            else d = sg;
+    for (int q = 0; q < 8; ++q) {
+        const float4 bb = b4[q];
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float x[4], d[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = q * 4 + t;
+            const int o = C * 32 + j;
+            x[t] = __uint_as_float(v[j]) + bv[t];
+            d[t] = x[t];
+            if (o < 5 + nc) {
+                const float sg = sigmoid_f(x[t]);
+                if (C == 0 && j == 0) d[t] = (sg * 2.0f + fgx) * det_stride;
+                else if (C == 0 && j == 1) d[t] = (sg * 2.0f + fgy) * det_stride;
+                else if (C == 0 && j == 2) { const float u = sg * 2.0f; d[t] = u * u * aw; }
+                else if (C == 0 && j == 3) { const float u = sg * 2.0f; d[t] = u * u * ah; }
+                else d[t] = sg;
+            }
         }
-        hr[j] = pack1(x, bf16);
-        hz[j] = pack1(d, bf16);
+        wr[2 * q] = pack2(x[0], x[1], bf16); wr[2 * q + 1] = pack2(x[2], x[3], bf16);
+        wz[2 * q] = pack2(d[0], d[1], bf16); wz[2 * q + 1] = pack2(d[2], d[3], bf16);
     }
     const int e0 = row * no + C * 32;     // first element of this thread's chunk inside the [128][no] block
     const int n_here = min(32, no - C * 32);
-    const int odd = e0 & 1;
     uint16_t* pr = stage_raw + e0;
     uint16_t* pz = stage_z + e0;
-    if (!odd) {
+    if (!(e0 & 1)) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             if (2 * j + 1 < n_here) {
-                *reinterpret_cast<uint32_t*>(pr + 2 * j) = static_cast<uint32_t>(hr[2 * j]) | (static_cast<uint32_t>(hr[2 * j + 1]) << 16);
-                *reinterpret_cast<uint32_t*>(pz + 2 * j) = static_cast<uint32_t>(hz[2 * j]) | (static_cast<uint32_t>(hz[2 * j + 1]) << 16);
+                *reinterpret_cast<uint32_t*>(pr + 2 * j) = wr[j];
+                *reinterpret_cast<uint32_t*>(pz + 2 * j) = wz[j];
             } else if (2 * j < n_here) {
-                pr[2 * j] = hr[2 * j];
-                pz[2 * j] = hz[2 * j];
+                pr[2 * j] = static_cast<uint16_t>(wr[j]);
+                pz[2 * j] = static_cast<uint16_t>(wz[j]);
             }
         }
-    } else {
-        if (n_here > 0) { pr[0] = hr[0]; pz[0] = hz[0]; }
+    } else {  // odd start: element 0 alone, then words made of (2j+1, 2j+2) = funnel shift of two neighbouring pair-words
+        if (n_here > 0) { pr[0] = static_cast<uint16_t>(wr[0]); pz[0] = static_cast<uint16_t>(wz[0]); }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             if (2 * j + 2 < n_here) {
-                *reinterpret_cast<uint32_t*>(pr + 2 * j + 1) = static_cast<uint32_t>(hr[2 * j + 1]) | (static_cast<uint32_t>(hr[2 * j + 2]) << 16);
-                *reinterpret_cast<uint32_t*>(pz + 2 * j + 1) = static_cast<uint32_t>(hz[2 * j + 1]) | (static_cast<uint32_t>(hz[2 * j + 2]) << 16);
+                *reinterpret_cast<uint32_t*>(pr + 2 * j + 1) = __funnelshift_r(wr[j], wr[j < 15 ? j + 1 : 15], 16);
+                *reinterpret_cast<uint32_t*>(pz + 2 * j + 1) = __funnelshift_r(wz[j], wz[j < 15 ? j + 1 : 15], 16);
             } else if (2 * j + 1 < n_here) {
-                pr[2 * j + 1] = hr[2 * j + 1];
-                pz[2 * j + 1] = hz[2 * j + 1];
+                pr[2 * j + 1] = static_cast<uint16_t>(wr[j] >> 16);
+                pz[2 * j + 1] = static_cast<uint16_t>(wz[j] >> 16);
             }
         }
     }
@@ -910,17 +917,26 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
             }
         }
         if (cl_sel != 1 && cl_sel != 2 && cl_sel != 4) cl_sel = 1;
-        // CTA-pair (cta_group::2) selection: Y5_CG2 = 0 off, 1 = layers with >= 256 output channels, 2 = also the 128-channel ones.
-        // A pair needs two M super-tiles per tile and enough pair-tiles to fill 74 pairs.
-        static const int cg2_mode = [] { const char* e = getenv("Y5_CG2"); return e ? atoi(e) : 0; }();
-        if (!d->block_n && cg2_mode > 0 && cg_sel == 1) {
+        // CTA-pair (cta_group::2) selection.  Measured on B200 (yolov5l, 64 x 640 x 640 bf16, profiles/r02_tile_store_sweep.md): pairs
+        // win wherever the weight tile is the larger smem operand -- every 3x3 layer with >= 128 output channels (-10..-22 %) and
+        // 1x1 layers with K >= 512 and >= 256 output channels (-3..-8 %); shallow 1x1 layers are store / latency bound and lose
+        // (+20..+70 %), they keep cta_group::1.  Y5_CG2: 0 = never, 1 = every layer with >= 256 channels, 2 = 1 + 128-channel
+        // layers, unset / 3 = the measured rule.  A pair needs >= ~60 pair-tiles to fill the 74 SM pairs.
+        static const int cg2_mode = [] { const char* e = getenv("Y5_CG2"); return e ? atoi(e) : 3; }();
+        if (!d->block_n && cg2_mode > 0 && cg_sel == 1 && d->out_c % 128 == 0) {
             const long long m_tiles = (M64 + kBlockM - 1) / kBlockM;
-            if (d->out_c >= 256 && d->out_c % 128 == 0) {
+            const bool linear = a_mode_sel == A_LINEAR;
+            const long long k_total = static_cast<long long>(g.kh) * g.kw * d->in_c;
+            bool want;
+            if (cg2_mode == 1) want = d->out_c >= 256;
+            else if (cg2_mode == 2) want = true;
+            else want = linear ? (k_total >= 512 && d->out_c >= 256) : true;
+            if (want && d->out_c >= 256) {
                 const int bn2 = d->out_c % 256 == 0 ? 256 : 128;
                 const long long pair_tiles = ((m_tiles + 1) / 2) * (d->out_c / bn2);
                 if (pair_tiles >= 60) { bn = bn2; mt_sel = 1; cg_sel = 2; cl_sel = 2; }
-            } else if (cg2_mode > 1 && d->out_c == 128) {
-                const int mt2 = a_mode_sel == A_LINEAR ? 1 : 2;
+            } else if (want && d->out_c == 128) {
+                const int mt2 = linear ? 1 : 2;
                 const long long pair_tiles = (m_tiles + 2 * mt2 - 1) / (2 * mt2);
                 if (pair_tiles >= 60) { bn = 128; mt_sel = mt2; cg_sel = 2; cl_sel = 2; }
             }
@@ -990,6 +1006,9 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     // layers; costs 32 KB of the pipeline's shared memory.  Y5_TMA_STORE = 0 off, 1 on (default), reserved bit 4 (16) forces it off in tests.
     static const int tma_store_mode = [] { const char* e = getenv("Y5_TMA_STORE"); return e ? atoi(e) : 1; }();
     p.tma_store = (tma_store_mode != 0 && !(d->reserved & 16)) ? 1 : 0;
+    // single-CTA TMA-im2col layers with 256-wide tiles are stage-starved (256x256 tiles fill the shared memory): the 32 KB of
+    // staging cost them 5-25 %; Y5_TMA_STORE=2 forces the staged store everywhere
+    if (tma_store_mode == 1 && cg_sel == 1 && p.a_mode == A_IM2COL && bn == 256) p.tma_store = 0;
     if (p.tma_store) {
         int ce;
         if (p.a_mode == A_PATCH) {
@@ -1008,7 +1027,12 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         if (ce) p.tma_store = 0;  // a view the copy engine cannot describe: the direct-store epilogue handles everything
     }
     if (!p.tma_store) pc.tmC = pc.tmA;  // unused, but must be a valid descriptor for the launch
-    if (int e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel, cg_sel)) { delete plan; return e2; }
+    int e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel, cg_sel);
+    if (e2 && p.tma_store) {  // no room for the staging tiles next to the pipeline stages: direct stores
+        p.tma_store = 0;
+        e2 = finish_plan(pc, bn, 0, mt_sel, cl_sel, cg_sel);
+    }
+    if (e2) { delete plan; return e2; }
     *out = plan;
     return 0;
 }
