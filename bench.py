@@ -762,16 +762,25 @@ def main():
         metric = "images/sec @640 (forward + NMS)"
     sub = {}
     if subs:
-        r2 = infer_leg(D, "yolov5s", 32, 640, "fp16", a.steps, a.warmup, extras=D.world == 1, cpu_base=False)
+        def leg(name, fn):
+            """A sub-record never takes the headline down with it: an exception (raised symmetrically on every rank: the legs run
+            the same code) is recorded in its place."""
+            try:
+                return fn()
+            except Exception as ex:  # noqa: BLE001
+                torch.cuda.empty_cache()
+                return {"unavailable": f"{type(ex).__name__}: {str(ex)[:300]}"} if D.rank == 0 else None
+
+        r2 = leg("config2", lambda: infer_leg(D, "yolov5s", 32, 640, "fp16", a.steps, a.warmup, extras=D.world == 1, cpu_base=False))
         if r2 is not None:
             r2["config"] = "BASELINE.json configs[1]: yolov5s forward + NMS, 32 images/GPU, 640x640, fp16 (per-GPU batch fixed)"
             sub["config2"] = r2
         if D.world > 1:
-            rw = infer_leg(D, model_name, images, size, dt, max(a.steps // 2, 5), 3, extras=False, cpu_base=False)
+            rw = leg("weak", lambda: infer_leg(D, model_name, images, size, dt, max(a.steps // 2, 5), 3, extras=False, cpu_base=False))
             if rw is not None:
                 rw["config"] = f"weak scaling of the main workload: {images} images PER GPU ({images * D.world} per step)"
-                sub["weak_scaling"] = {k: rw[k] for k in ("value", "unit", "ms_per_step", "e2e", "config")}
-        rt = train_leg(D, "yolov5m", 16, 640, "fp16", max(a.steps // 2, 8), 3, extras=D.world == 1)
+                sub["weak_scaling"] = {k: rw[k] for k in ("value", "unit", "ms_per_step", "e2e", "config", "unavailable") if k in rw}
+        rt = leg("train", lambda: train_leg(D, "yolov5m", 16, 640, "fp16", max(a.steps // 2, 8), 3, extras=D.world == 1))
         if rt is not None:
             rt["config"] = (f"BASELINE.json configs[3]: yolov5m training step, 16 images/GPU x {D.world} = {16 * D.world} per step, 640x640, AMP fp16"
                             + (", DDP gradient all-reduce" if D.world > 1 else ""))

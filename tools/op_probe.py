@@ -44,9 +44,11 @@ else:
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 run()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: only the probed launches are captured
 e0.record()
 for _ in range(reps):
     run()
 e1.record()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print(f"{name} {want}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per launch (back to back, {reps} reps)")

@@ -138,8 +138,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {  // arrive (count 1) on a barrier anywhere in the cluster
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+// arrive (count 1) on a barrier anywhere in the cluster.  Default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive
+// does for the accumulator-empty hand-shake of CTA pairs: the tcgen05.ld results were waited for and fenced
+// (tcgen05.fence::before_thread_sync) by the arriving warp; `.release.cluster` here made ptxas emit MEMBAR.ALL.GPU + ERRBAR per
+// tile and warp (8 % of the stall samples of a pair-mode layer under ncu).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
