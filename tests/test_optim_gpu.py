@@ -199,6 +199,7 @@ def test_graphed_train_step_with_loss_scaling_ema_and_schedule(cuda):
     step = GraphedTrainStep(ma, ComputeLoss(ma), oa, batch=2, size=128, ema=ea)
     lb, sb = ComputeLoss(mb), torch.amp.GradScaler("cuda")
     items_a = []
+    w0 = torch.cat([v.detach().flatten() for v in ma.parameters()]).clone()
     for i in range(3):
         lr = 0.01 * (1 + i)
         for g_ in oa.param_groups + ob.param_groups:
@@ -212,15 +213,16 @@ def test_graphed_train_step_with_loss_scaling_ema_and_schedule(cuda):
         ob.fused_step(scaler=sb, max_norm=10.0, ema=eb, model=mb)
         ob.zero_grad()
         assert torch.allclose(items_a[-1], items_b, rtol=3e-2, atol=1e-4), (i, items_a[-1], items_b)
+        if i == 0:
+            # after ONE step from identical weights the two runs differ only by reduction order (weight-gradient red.add, fp16
+            # atomics of the loss gradient): a few percent of the step at most.  Later steps of this random little problem are
+            # chaotic (tools/train_diag.py), so only their loss items / scale / counters are compared.
+            wa = torch.cat([v.detach().flatten() for v in ma.parameters()])
+            wb = torch.cat([v.detach().flatten() for v in mb.parameters()])
+            moved = float((wb - w0).norm())
+            assert moved > 0 and float((wa - wb).norm()) <= 0.05 * moved, (float((wa - wb).norm()), moved)
+            ema_a = torch.cat([v.flatten() for v in ea.ema.parameters()])
+            ema_b = torch.cat([v.flatten() for v in eb.ema.parameters()])
+            assert float((ema_a - w0).norm()) > 0 and float((ema_a - ema_b).norm()) <= 0.05 * float((ema_b - w0).norm())
     assert ea.updates == eb.updates == 3 and float(step.scaler.get_scale()) == float(sb.get_scale())
-    # two independent runs (graph replay vs eager) of a chaotic little training problem: same walk, not the same bits
-    w0 = torch.cat([v.flatten() for v in _train_setup(cuda, seed=1)[0].parameters()])
-    wa = torch.cat([v.detach().flatten() for v in ma.parameters()])
-    wb = torch.cat([v.detach().flatten() for v in mb.parameters()])
-    moved = float((wb - w0).norm())
-    assert moved > 0 and float((wa - wb).norm()) <= 0.1 * moved, (float((wa - wb).norm()), moved)
-    ema_a = torch.cat([v.flatten() for v in ea.ema.parameters()])
-    ema_b = torch.cat([v.flatten() for v in eb.ema.parameters()])
-    ema_moved = float((ema_b - w0).norm())
-    assert ema_moved > 0 and float((ema_a - ema_b).norm()) <= 0.1 * ema_moved
-    assert int(ma.model[0].bn.num_batches_tracked) == 3
+    assert int(ma.model[0].bn.num_batches_tracked) == 3 and all(bool(torch.isfinite(v).all()) for v in ma.parameters())

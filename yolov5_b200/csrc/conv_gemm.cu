@@ -64,6 +64,7 @@ struct ConvParams {
     int a_mode;
     int Ho, Wo, HoWo, stride, pad_h, pad_w;
     int tw, th, tiles_x, tiles_y;  // PATCH: spatial sub-tile th x tw (= 128 pixels), sub-tiles per image
+    float rcp_per_img, rcp_tiles_x, rcp_HoWo, rcp_Wo;  // reciprocals for fdiv(): exact small-integer division in ~7 instructions
     int a_stages, b_stages;
     int tma_store;              // epilogue: per-warp swizzled smem staging + cp.async.bulk.tensor store instead of row-strided STG
     int c_bw, c_bh;             // PATCH + tma_store: store box = c_bw pixels x c_bh rows (c_bw * c_bh = 32)
@@ -111,6 +112,17 @@ __host__ __device__ inline SmemLayout smem_layout(int epi, int no, int bias_n, i
     o += 16;
     L.total = o;
     return L;
+}
+
+// floor(n / d) for 0 <= n < 2^23, d >= 1, with rd = 1.0f / d: the float estimate is off by at most one, corrected exactly.
+// (ptxas expands a 32-bit integer division into ~30 instructions; the tile decodes below run per tile in every role.)
+__device__ __forceinline__ int fdiv(int n, int d, float rd) {
+    if (n >= (1 << 23)) return n / d;  // beyond float's exact-integer range: the slow path (warp-uniform, rare)
+    int q = __float2int_rz(__int2float_rz(n) * rd);
+    const int r = n - q * d;
+    if (r >= d) ++q;
+    else if (r < 0) --q;
+    return q;
 }
 
 // Detect-head epilogue for one 32-column chunk of a row: logits -> raw + decoded (models/yolo.py:103-109), both written into the
@@ -235,7 +247,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1) { if (CG == 2) tmem_alloc_cg2(tmem_ptr_smem, kTmemCols); else tmem_alloc(tmem_ptr_smem, kTmemCols); }
     if (warp >= 2)  // whole folded-BN bias vector once: no per-tile global loads on the epilogue's critical path
-        for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) sBias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
+        for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) {
+            // SiLU layers keep HALF the bias: the epilogue forms h = (acc + b) / 2 with one FMA and silu = h + h * tanh(h)
+            const float b = i < p.N ? __ldg(p.bias + i) : 0.0f;
+            sBias[i] = (EPI == 0 && p.act) ? 0.5f * b : b;
+        }
     tc_fence_before();
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
@@ -249,6 +265,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // tiles are (group of csize M super-tiles, N tile); this CTA takes super-tile group*csize + crank
     const int num_tiles = ((p.num_m_super + static_cast<int>(csize) - 1) / static_cast<int>(csize)) * p.num_n_tiles;
     const int tile0 = blockIdx.x / csize, tile_step = gridDim.x / csize;
+    // tile -> (M group tq, N tile tr) kept incrementally: one division per kernel instead of two per tile and role
+    const int nn = p.num_n_tiles;
+    const int step_q = tile_step / nn, step_r = tile_step - step_q * nn;
+    const int tq0 = tile0 / nn, tr0 = tile0 - tq0 * nn;
+#define Y5_NEXT_TILE(tq, tr)            \
+    do {                                \
+        tq += step_q;                   \
+        tr += step_r;                   \
+        if (tr >= nn) { tr -= nn; ++tq; } \
+    } while (0)
     const uint32_t row_bytes = p.block_k * 2;
     const bool patch = p.a_mode == A_PATCH;
     // K iteration: "A groups" each feeding `grp` consecutive B tiles.
@@ -264,9 +290,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // vote / elect / R2UR waterfall)
             int as = 0, bs = 0;
             uint32_t aph = 0, bph = 0;
+            int tq = tq0, tr = tr0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int ms = (tile / p.num_n_tiles) * csize + crank;
-                const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+                const int ms = tq * csize + crank;
+                const int n0 = tr * BLOCK_N;
+                Y5_NEXT_TILE(tq, tr);
                 int img[MT], y0[MT], x0[MT];  // IM2COL: base pixel of the first window; PATCH: sub-tile origin
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi) {
@@ -274,16 +302,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     img[mi] = y0[mi] = x0[mi] = 0;
                     if (p.a_mode == A_IM2COL) {
                         const int m0 = mt * kBlockM;
-                        img[mi] = m0 / p.HoWo;
+                        img[mi] = fdiv(m0, p.HoWo, p.rcp_HoWo);
                         const int rem = m0 - img[mi] * p.HoWo;
-                        const int oy = rem / p.Wo;
+                        const int oy = fdiv(rem, p.Wo, p.rcp_Wo);
                         y0[mi] = oy * p.stride - p.pad_h;
                         x0[mi] = (rem - oy * p.Wo) * p.stride - p.pad_w;
                     } else if (patch) {
                         const int per_img = p.tiles_x * p.tiles_y;
-                        img[mi] = mt / per_img;
+                        img[mi] = fdiv(mt, per_img, p.rcp_per_img);
                         const int rem = mt - img[mi] * per_img;
-                        const int ty = rem / p.tiles_x;
+                        const int ty = fdiv(rem, p.tiles_x, p.rcp_tiles_x);
                         y0[mi] = ty * p.th - p.pad_h;
                         x0[mi] = (rem - ty * p.tiles_x) * p.tw - p.pad_w;
                     }
@@ -432,10 +460,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ry = row >> tw_shift, rx = row & ((1 << tw_shift) - 1);
         int acc = 0, head_set = 0;
         uint32_t acc_phase = 0;
+        int tq = tq0, tr = tr0;
+        const bool staged = EPI == 0 && p.tma_store != 0;
+        const bool any_res = p.res != nullptr;
+        uint8_t* stg = smem + L.off_out + ew * 2048;  // this warp's [32 rows][32 channels] tile, 64-byte rows, SWIZZLE_64B
+        const int pos0 = quarter * 32;                // first tile position of this warp (PATCH: th x tw block, row-major)
+        const int y_in = pos0 >> tw_shift, x_in = pos0 & ((1 << tw_shift) - 1);
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-            const int ms = (tile / p.num_n_tiles) * csize + crank;
-            const int nt = tile % p.num_n_tiles;
+            const int ms = tq * csize + crank;
+            const int nt = tr;
             const int n0 = nt * BLOCK_N;
+            Y5_NEXT_TILE(tq, tr);
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols;
 
             if (EPI == 0) {
@@ -446,23 +481,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int mi = c / kChunksPerSub;             // sub-tile of this chunk
                     const int col = (c - mi * kChunksPerSub) * 32;  // first column inside the N tile
                     const int mt = ms * MT + mi;
-                    long long gpix = -1;                          // global output pixel of this thread's row
+                    // warp-uniform decode of the sub-tile (PATCH: image + origin of the th x tw block)
+                    int img = 0, oy0 = 0, ox0 = 0;
                     if (patch) {
-                        // warp-uniform tile decode (two divisions per chunk); the thread's offset inside the th x tw tile
-                        // (ry, rx) is loop invariant because tw is a power of two
-                        const int img = mt / per_img;
+                        img = fdiv(mt, per_img, p.rcp_per_img);
                         const int rem = mt - img * per_img;
-                        const int tyi = rem / p.tiles_x;
-                        const int oy = tyi * p.th + ry, ox = (rem - tyi * p.tiles_x) * p.tw + rx;
-                        if (mt < p.num_m_tiles && oy < p.Ho && ox < p.Wo) gpix = static_cast<long long>(img) * p.HoWo + oy * p.Wo + ox;
-                    } else {
-                        const long long m = static_cast<long long>(mt) * kBlockM + row;
-                        if (m < p.M) gpix = m;
+                        const int tyi = fdiv(rem, p.tiles_x, p.rcp_tiles_x);
+                        oy0 = tyi * p.th;
+                        ox0 = (rem - tyi * p.tiles_x) * p.tw;
+                    }
+                    // this thread's global output pixel: only the residual read and the direct-store path need it
+                    long long gpix = -1;
+                    if (any_res || !staged) {
+                        if (patch) {
+                            const int oy = oy0 + ry, ox = ox0 + rx;  // (ry, rx) is loop invariant because tw is a power of two
+                            if (mt < p.num_m_tiles && oy < p.Ho && ox < p.Wo) gpix = static_cast<long long>(img) * p.HoWo + oy * p.Wo + ox;
+                        } else {
+                            const long long m = static_cast<long long>(mt) * kBlockM + row;
+                            if (m < p.M) gpix = m;
+                        }
                     }
                     const bool live = gpix >= 0;
                     // residual for this thread's 32 output channels: issued before the TMEM load so its latency overlaps
                     uint4 rv[4];
-                    const bool has_res = p.res != nullptr && live;
+                    const bool has_res = any_res && live;
                     if (has_res) {
                         const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (gpix * p.res_pitch + n0 + col) * 2;
 #pragma unroll
@@ -471,21 +513,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     uint32_t v[32];
                     tmem_ld_32x32(t_row + c * 32, v);
-                    tmem_ld_wait();
-                    uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (gpix * p.out_pitch + n0 + col) * 2;
-                    const bool staged = p.tma_store != 0;
-                    uint8_t* stg = smem + L.off_out + ew * 2048;  // this warp's [32 rows][32 channels] tile, 64-byte rows, SWIZZLE_64B
                     if (staged) {  // the previous bulk store of this warp must have finished READING the staging tile
                         if (lane == 0) tma_store_wait_read0();
                         __syncwarp();
                     }
+                    tmem_ld_wait();
+                    uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (gpix * p.out_pitch + n0 + col) * 2;
+                    const float4* b4 = reinterpret_cast<const float4*>(sBias + n0 + col);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
+                        const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float x = __uint_as_float(v[g * 8 + j]) + sBias[n0 + col + g * 8 + j];
-                            f[j] = p.act ? silu_f(x) : x;
+                            const float a = __uint_as_float(v[g * 8 + j]);
+                            if (p.act) {  // bv holds bias / 2 (see the preload): 3 instructions per element
+                                const float h = fmaf(a, 0.5f, bv[j]);
+                                f[j] = silu_from_half(h);
+                            } else {
+                                f[j] = a + bv[j];
+                            }
                         }
                         if (has_res) {
                             const uint32_t rr[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
@@ -510,21 +558,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0 && mt < p.num_m_tiles && n0 + col < p.N) {
-                            if (patch) {
-                                const int img = mt / per_img;
-                                const int rem = mt - img * per_img;
-                                const int tyi = rem / p.tiles_x;
-                                const int pos0 = quarter * 32;
-                                const int y_in = pos0 >> tw_shift, x_in = pos0 & ((1 << tw_shift) - 1);
-                                tma_store_4d(&tmC, stg, n0 + col, (rem - tyi * p.tiles_x) * p.tw + x_in, tyi * p.th + y_in, img);
-                            } else {
-                                tma_store_2d(&tmC, stg, n0 + col, mt * kBlockM + quarter * 32);
-                            }
+                            if (patch) tma_store_4d(&tmC, stg, n0 + col, ox0 + x_in, oy0 + y_in, img);
+                            else tma_store_2d(&tmC, stg, n0 + col, mt * kBlockM + pos0);
                             tma_store_commit();
                         }
                     }
                 }
-                if (p.tma_store && lane == 0) tma_store_wait_read0();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {  // this warp is done with the accumulator set (pair mode: tell the leader, it issues the MMAs)
@@ -546,9 +585,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m0 = ms * kBlockM;
                 const int m = m0 + row;
                 int gx = 0, gy = 0;
-                if (m < p.M) { const int pix = m % p.HoWo; gy = pix / p.nx; gx = pix - gy * p.nx; }
+                if (m < p.M) { const int pix = m - fdiv(m, p.HoWo, p.rcp_HoWo) * p.HoWo; gy = fdiv(pix, p.nx, p.rcp_Wo); gx = pix - gy * p.nx; }
                 const int rows_here = min(kBlockM, p.M - m0);
-                const int b_lo = m0 / p.HoWo, b_hi = (m0 + rows_here - 1) / p.HoWo;
+                const int b_lo = fdiv(m0, p.HoWo, p.rcp_HoWo), b_hi = fdiv(m0 + rows_here - 1, p.HoWo, p.rcp_HoWo);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 if (slot * 32 < no) {
@@ -951,6 +990,8 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     p.N = d->out_c;
     p.kh = g.kh; p.kw = g.kw;
     p.Ho = g.Ho; p.Wo = g.Wo; p.HoWo = g.Ho * g.Wo;
+    p.rcp_HoWo = 1.0f / static_cast<float>(p.HoWo);
+    p.rcp_Wo = 1.0f / static_cast<float>(p.Wo);
     p.stride = d->stride;
     p.pad_h = g.pad_h; p.pad_w = g.pad_w;
     p.is_bf16 = d->dtype == Y5_BF16;
@@ -985,6 +1026,8 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         p.th = 128 / best_tw;
         p.tiles_x = (g.Wo + p.tw - 1) / p.tw;
         p.tiles_y = (g.Ho + p.th - 1) / p.th;
+        p.rcp_tiles_x = 1.0f / static_cast<float>(p.tiles_x);
+        p.rcp_per_img = 1.0f / static_cast<float>(p.tiles_x * p.tiles_y);
         p.num_m_tiles = d->batch * p.tiles_x * p.tiles_y;
         p.a_sub_bytes = (p.th + g.kh - 1) * p.tw * row_bytes;
         cuuint64_t dims[4] = {(cuuint64_t)d->in_c, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->batch};
@@ -1089,6 +1132,8 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     p.N = d->na * kHeadN;  // weights / bias are packed with every anchor padded to kHeadN rows
     p.kh = p.kw = 1;
     p.Ho = d->ny; p.Wo = d->nx; p.HoWo = d->ny * d->nx;
+    p.rcp_HoWo = 1.0f / static_cast<float>(p.HoWo);
+    p.rcp_Wo = 1.0f / static_cast<float>(p.Wo);
     p.stride = 1;
     p.is_bf16 = d->dtype == Y5_BF16;
     p.bias = d->bias;
