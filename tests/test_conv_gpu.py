@@ -86,7 +86,7 @@ def test_conv_cluster_multicast(cuda, bn, mt2, case, a_mode):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("bn,mt2", [(128, False), (128, True), (256, False)])
+@pytest.mark.parametrize("bn,mt2", [(128, False), (128, True), (256, False), (256, True)])
 @pytest.mark.parametrize("case,a_mode", [((4, 40, 40, 64, 256, 3, 1, 1), 2), ((4, 40, 40, 64, 256, 3, 1, 1), 1), ((5, 24, 24, 128, 512, 1, 1, 0), 0),
                                          ((3, 40, 40, 128, 384, 3, 2, 1), 0), ((2, 80, 80, 128, 128, 3, 1, 1), 2), ((1, 20, 20, 512, 512, 3, 1, 1), 0)])
 def test_conv_cta_pairs(cuda, dtype, bn, mt2, case, a_mode):

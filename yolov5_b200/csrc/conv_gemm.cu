@@ -834,6 +834,7 @@ int run_plan(const PlanCommon& pc, cudaStream_t st) {
         case 101281: e = launch_conv<128, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 101282: e = launch_conv<128, 0, 2, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 102561: e = launch_conv<256, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
+        case 102562: e = launch_conv<256, 0, 2, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 324: e = launch_conv<32, 0, 4>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
         case 642: e = launch_conv<64, 0, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
         case 1281: e = launch_conv<128, 0, 1>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, pc.cluster, pc.smem_bytes, st); break;
@@ -974,6 +975,11 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
                 const int bn2 = d->out_c % 256 == 0 ? 256 : 128;
                 const long long pair_tiles = ((m_tiles + 1) / 2) * (d->out_c / bn2);
                 if (pair_tiles >= 60) { bn = bn2; mt_sel = 1; cg_sel = 2; cl_sel = 2; }
+                // 512 x 256 pair tiles (two sub-tiles per CTA, all 512 TMEM columns, single-buffered accumulators): half the weight
+                // bytes per flop again.  The 3x3 layers with >= 256 channels move ~7 TB/s between L2 and the SMs in 256 x 256
+                // pair tiles (ncu: l1tex__m_xbar2l1tex_read_bytes), the ceiling seen on this part.  Y5_CG2_MT2=1 enables (A/B).
+                static const bool mt2_pairs = [] { const char* e = getenv("Y5_CG2_MT2"); return e && e[0] == '1'; }();
+                if (mt2_pairs && cg_sel == 2 && bn == 256 && !linear && ((m_tiles + 3) / 4) * (d->out_c / 256) >= 60) mt_sel = 2;
             } else if (want && d->out_c == 128) {
                 const int mt2 = linear ? 1 : 2;
                 const long long pair_tiles = (m_tiles + 2 * mt2 - 1) / (2 * mt2);
