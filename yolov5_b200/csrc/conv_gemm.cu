@@ -83,6 +83,7 @@ struct ConvParams {
     void* raw;
     void* z;
     int na, no, nc, nx, z_rows, z_row0;
+    int head_cb[4], head_cn[4]; // EPI 1: first column / column count of each of the 4 epilogue column slots (balanced, multiples of 4)
     float det_stride;
     float anchor_wh[8];
 };
@@ -129,38 +130,41 @@ __device__ __forceinline__ int fdiv(int n, int d, float rd) {
 // shared-memory staging blocks that mirror the global [pixel][no] layout.  Values are packed in pairs and stored as 32-bit
 // words: a row starts on an odd 16-bit element when row*no is odd (no = 85), so the pairing shifts by one for those rows and
 // the two boundary elements go out as 16-bit stores (the neighbouring halves of those words belong to other threads).
-template <int C>
-__device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int no, int nc, float fgx, float fgy,
-                                           float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
+template <bool FIRST>
+__device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int cb, int cn, int no, int nc, float fgx,
+                                           float fgy, float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
                                            uint16_t* __restrict__ stage_z, int row) {
-    // words wr[j] / wz[j] = elements (2j, 2j+1) of this chunk, converted two at a time (cvt.rn.f16x2 / bf16x2)
+    // this warp's columns [cb, cb + cn) of the anchor's `no` outputs (cb % 4 == 0, cn <= 32); FIRST: the slot that holds x, y, w, h.
+    // words wr[j] / wz[j] = elements (2j, 2j+1) of the chunk, converted two at a time (cvt.rn.f16x2 / bf16x2); groups of four
+    // elements beyond cn are skipped with a warp-uniform branch
     uint32_t wr[16], wz[16];
-    const float4* b4 = reinterpret_cast<const float4*>(bias + C * 32);  // 128-byte aligned: bias vector base and C*32 floats
+    const float4* b4 = reinterpret_cast<const float4*>(bias + cb);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 bb = b4[q];
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-        float x[4], d[4];
+        if (q * 4 < cn) {
+            const float4 bb = b4[q];
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+            float x[4], d[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int j = q * 4 + t;
-            const int o = C * 32 + j;
-            x[t] = __uint_as_float(v[j]) + bv[t];
-            d[t] = x[t];
-            if (o < 5 + nc) {
-                const float sg = sigmoid_f(x[t]);
-                if (C == 0 && j == 0) d[t] = (sg * 2.0f + fgx) * det_stride;
-                else if (C == 0 && j == 1) d[t] = (sg * 2.0f + fgy) * det_stride;
-                else if (C == 0 && j == 2) { const float u = sg * 2.0f; d[t] = u * u * aw; }
-                else if (C == 0 && j == 3) { const float u = sg * 2.0f; d[t] = u * u * ah; }
-                else d[t] = sg;
+            for (int t = 0; t < 4; ++t) {
+                const int j = q * 4 + t;
+                x[t] = __uint_as_float(v[j]) + bv[t];
+                d[t] = x[t];
+                if (cb + j < 5 + nc) {
+                    const float sg = sigmoid_f(x[t]);
+                    if (FIRST && j == 0) d[t] = (sg * 2.0f + fgx) * det_stride;
+                    else if (FIRST && j == 1) d[t] = (sg * 2.0f + fgy) * det_stride;
+                    else if (FIRST && j == 2) { const float u = sg * 2.0f; d[t] = u * u * aw; }
+                    else if (FIRST && j == 3) { const float u = sg * 2.0f; d[t] = u * u * ah; }
+                    else d[t] = sg;
+                }
             }
+            wr[2 * q] = pack2(x[0], x[1], bf16); wr[2 * q + 1] = pack2(x[2], x[3], bf16);
+            wz[2 * q] = pack2(d[0], d[1], bf16); wz[2 * q + 1] = pack2(d[2], d[3], bf16);
         }
-        wr[2 * q] = pack2(x[0], x[1], bf16); wr[2 * q + 1] = pack2(x[2], x[3], bf16);
-        wz[2 * q] = pack2(d[0], d[1], bf16); wz[2 * q + 1] = pack2(d[2], d[3], bf16);
     }
-    const int e0 = row * no + C * 32;     // first element of this thread's chunk inside the [128][no] block
-    const int n_here = min(32, no - C * 32);
+    const int e0 = row * no + cb;         // first element of this thread's chunk inside the [128][no] block
+    const int n_here = min(cn, no - cb);
     uint16_t* pr = stage_raw + e0;
     uint16_t* pz = stage_z + e0;
     if (!(e0 & 1)) {
@@ -590,19 +594,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int b_lo = fdiv(m0, p.HoWo, p.rcp_HoWo), b_hi = fdiv(m0 + rows_here - 1, p.HoWo, p.rcp_HoWo);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                if (slot * 32 < no) {
+                {   // the anchor's `no` columns are split evenly over the 4 column slots (85 -> 24 + 20 + 20 + 21): all 16 warps work
+                    const int cb = p.head_cb[slot], cn = p.head_cn[slot];
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + slot * 32, v);
+                    tmem_ld_32x32(t_row + cb, v);
                     tmem_ld_wait();
                     const float fgx = static_cast<float>(gx) - 0.5f, fgy = static_cast<float>(gy) - 0.5f;
-                    // column chunk as a compile-time constant: the xy / wh special cases exist only in chunk 0's code
-                    switch (slot) {
-                        case 0: head_chunk<0>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, p.anchor_wh[a * 2], p.anchor_wh[a * 2 + 1], bf16,
-                                              stage_raw, stage_z, row); break;
-                        case 1: head_chunk<1>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
-                        case 2: head_chunk<2>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
-                        default: head_chunk<3>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
-                    }
+                    if (slot == 0)
+                        head_chunk<true>(v, sBias + n0, cb, cn, no, p.nc, fgx, fgy, p.det_stride, p.anchor_wh[a * 2], p.anchor_wh[a * 2 + 1], bf16,
+                                         stage_raw, stage_z, row);
+                    else
+                        head_chunk<false>(v, sBias + n0, cb, cn, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -976,10 +978,14 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
                 const long long pair_tiles = ((m_tiles + 1) / 2) * (d->out_c / bn2);
                 if (pair_tiles >= 60) { bn = bn2; mt_sel = 1; cg_sel = 2; cl_sel = 2; }
                 // 512 x 256 pair tiles (two sub-tiles per CTA, all 512 TMEM columns, single-buffered accumulators): half the weight
-                // bytes per flop again.  The 3x3 layers with >= 256 channels move ~7 TB/s between L2 and the SMs in 256 x 256
-                // pair tiles (ncu: l1tex__m_xbar2l1tex_read_bytes), the ceiling seen on this part.  Y5_CG2_MT2=1 enables (A/B).
-                static const bool mt2_pairs = [] { const char* e = getenv("Y5_CG2_MT2"); return e && e[0] == '1'; }();
-                if (mt2_pairs && cg_sel == 2 && bn == 256 && !linear && ((m_tiles + 3) / 4) * (d->out_c / 256) >= 60) mt_sel = 2;
+                // bytes per flop again.  Measured (profiles/r02_tile_store_sweep.md): -6..-19 % on the stride-2 TMA-im2col layers when
+                // there are >= ~150 such tiles (model.3/5/7/18 of yolov5l), +17..+32 % on shifted-patch layers (their activation
+                // patches leave room for two stages only) -> im2col stride >= 2 only.  Y5_CG2_MT2=0 off, 1 = every non-1x1 layer.
+                static const int mt2_pairs = [] { const char* e = getenv("Y5_CG2_MT2"); return e ? atoi(e) : 2; }();
+                const long long tiles_mt2 = ((m_tiles + 3) / 4) * (d->out_c / 256);
+                if (mt2_pairs && cg_sel == 2 && bn == 256 && !linear &&
+                    (mt2_pairs == 1 ? tiles_mt2 >= 60 : (a_mode_sel == A_IM2COL && d->stride >= 2 && tiles_mt2 >= 150)))
+                    mt_sel = 2;
             } else if (want && d->out_c == 128) {
                 const int mt2 = linear ? 1 : 2;
                 const long long pair_tiles = (m_tiles + 2 * mt2 - 1) / (2 * mt2);
@@ -1149,6 +1155,19 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     p.z_rows = d->z_rows; p.z_row0 = d->z_row0;
     p.det_stride = d->stride;
     for (int i = 0; i < 8; ++i) p.anchor_wh[i] = d->anchor_wh[i];
+    {   // column slots of the epilogue: starts at multiples of 4 (16-byte bias loads), at most 32 columns each, slot 0 holds x, y, w, h
+        int cb = 0, remaining = d->no;
+        for (int s = 0; s < 4; ++s) {
+            int cn = (remaining + (4 - s) - 1) / (4 - s);  // even share of what is left ...
+            cn = (cn + 3) & ~3;                              // ... rounded up to 4
+            if (cn > 32) cn = 32;
+            if (cn > remaining || s == 3) cn = remaining;
+            p.head_cb[s] = cb;
+            p.head_cn[s] = cn;
+            cb += cn;
+            remaining -= cn;
+        }
+    }
     p.a_mode = A_LINEAR;
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
