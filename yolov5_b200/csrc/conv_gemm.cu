@@ -83,7 +83,6 @@ struct ConvParams {
     void* raw;
     void* z;
     int na, no, nc, nx, z_rows, z_row0;
-    int head_cb[4], head_cn[4]; // EPI 1: first column / column count of each of the 4 epilogue column slots (balanced, multiples of 4)
     float det_stride;
     float anchor_wh[8];
 };
@@ -130,41 +129,38 @@ __device__ __forceinline__ int fdiv(int n, int d, float rd) {
 // shared-memory staging blocks that mirror the global [pixel][no] layout.  Values are packed in pairs and stored as 32-bit
 // words: a row starts on an odd 16-bit element when row*no is odd (no = 85), so the pairing shifts by one for those rows and
 // the two boundary elements go out as 16-bit stores (the neighbouring halves of those words belong to other threads).
-template <bool FIRST>
-__device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int cb, int cn, int no, int nc, float fgx,
-                                           float fgy, float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
+template <int C>
+__device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float* __restrict__ bias, int no, int nc, float fgx, float fgy,
+                                           float det_stride, float aw, float ah, bool bf16, uint16_t* __restrict__ stage_raw,
                                            uint16_t* __restrict__ stage_z, int row) {
-    // this warp's columns [cb, cb + cn) of the anchor's `no` outputs (cb % 4 == 0, cn <= 32); FIRST: the slot that holds x, y, w, h.
-    // words wr[j] / wz[j] = elements (2j, 2j+1) of the chunk, converted two at a time (cvt.rn.f16x2 / bf16x2); groups of four
-    // elements beyond cn are skipped with a warp-uniform branch
+    // words wr[j] / wz[j] = elements (2j, 2j+1) of this chunk, converted two at a time (cvt.rn.f16x2 / bf16x2)
     uint32_t wr[16], wz[16];
-    const float4* b4 = reinterpret_cast<const float4*>(bias + cb);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + C * 32);  // 128-byte aligned: bias vector base and C*32 floats
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        if (q * 4 < cn) {
-            const float4 bb = b4[q];
-            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-            float x[4], d[4];
+        const float4 bb = b4[q];
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float x[4], d[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int j = q * 4 + t;
-                x[t] = __uint_as_float(v[j]) + bv[t];
-                d[t] = x[t];
-                if (cb + j < 5 + nc) {
-                    const float sg = sigmoid_f(x[t]);
-                    if (FIRST && j == 0) d[t] = (sg * 2.0f + fgx) * det_stride;
-                    else if (FIRST && j == 1) d[t] = (sg * 2.0f + fgy) * det_stride;
-                    else if (FIRST && j == 2) { const float u = sg * 2.0f; d[t] = u * u * aw; }
-                    else if (FIRST && j == 3) { const float u = sg * 2.0f; d[t] = u * u * ah; }
-                    else d[t] = sg;
-                }
+        for (int t = 0; t < 4; ++t) {
+            const int j = q * 4 + t;
+            const int o = C * 32 + j;
+            x[t] = __uint_as_float(v[j]) + bv[t];
+            d[t] = x[t];
+            if (o < 5 + nc) {
+                const float sg = sigmoid_f(x[t]);
+                if (C == 0 && j == 0) d[t] = (sg * 2.0f + fgx) * det_stride;
+                else if (C == 0 && j == 1) d[t] = (sg * 2.0f + fgy) * det_stride;
+                else if (C == 0 && j == 2) { const float u = sg * 2.0f; d[t] = u * u * aw; }
+                else if (C == 0 && j == 3) { const float u = sg * 2.0f; d[t] = u * u * ah; }
+                else d[t] = sg;
             }
-            wr[2 * q] = pack2(x[0], x[1], bf16); wr[2 * q + 1] = pack2(x[2], x[3], bf16);
-            wz[2 * q] = pack2(d[0], d[1], bf16); wz[2 * q + 1] = pack2(d[2], d[3], bf16);
         }
+        wr[2 * q] = pack2(x[0], x[1], bf16); wr[2 * q + 1] = pack2(x[2], x[3], bf16);
+        wz[2 * q] = pack2(d[0], d[1], bf16); wz[2 * q + 1] = pack2(d[2], d[3], bf16);
     }
-    const int e0 = row * no + cb;         // first element of this thread's chunk inside the [128][no] block
-    const int n_here = min(cn, no - cb);
+    const int e0 = row * no + C * 32;     // first element of this thread's chunk inside the [128][no] block
+    const int n_here = min(32, no - C * 32);
     uint16_t* pr = stage_raw + e0;
     uint16_t* pz = stage_z + e0;
     if (!(e0 & 1)) {
@@ -594,17 +590,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int b_lo = fdiv(m0, p.HoWo, p.rcp_HoWo), b_hi = fdiv(m0 + rows_here - 1, p.HoWo, p.rcp_HoWo);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                {   // the anchor's `no` columns are split evenly over the 4 column slots (85 -> 24 + 20 + 20 + 21): all 16 warps work
-                    const int cb = p.head_cb[slot], cn = p.head_cn[slot];
+                if (slot * 32 < no) {
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + cb, v);
+                    tmem_ld_32x32(t_row + slot * 32, v);
                     tmem_ld_wait();
                     const float fgx = static_cast<float>(gx) - 0.5f, fgy = static_cast<float>(gy) - 0.5f;
-                    if (slot == 0)
-                        head_chunk<true>(v, sBias + n0, cb, cn, no, p.nc, fgx, fgy, p.det_stride, p.anchor_wh[a * 2], p.anchor_wh[a * 2 + 1], bf16,
-                                         stage_raw, stage_z, row);
-                    else
-                        head_chunk<false>(v, sBias + n0, cb, cn, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row);
+                    // column chunk as a compile-time constant: the xy / wh special cases exist only in chunk 0's code
+                    switch (slot) {
+                        case 0: head_chunk<0>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, p.anchor_wh[a * 2], p.anchor_wh[a * 2 + 1], bf16,
+                                              stage_raw, stage_z, row); break;
+                        case 1: head_chunk<1>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
+                        case 2: head_chunk<2>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
+                        default: head_chunk<3>(v, sBias + n0, no, p.nc, fgx, fgy, p.det_stride, 0.f, 0.f, bf16, stage_raw, stage_z, row); break;
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1155,19 +1153,6 @@ extern "C" Y5_API int y5_detect_plan_create(const y5_detect_desc* d, y5_detect_p
     p.z_rows = d->z_rows; p.z_row0 = d->z_row0;
     p.det_stride = d->stride;
     for (int i = 0; i < 8; ++i) p.anchor_wh[i] = d->anchor_wh[i];
-    {   // column slots of the epilogue: starts at multiples of 4 (16-byte bias loads), at most 32 columns each, slot 0 holds x, y, w, h
-        int cb = 0, remaining = d->no;
-        for (int s = 0; s < 4; ++s) {
-            int cn = (remaining + (4 - s) - 1) / (4 - s);  // even share of what is left ...
-            cn = (cn + 3) & ~3;                              // ... rounded up to 4
-            if (cn > 32) cn = 32;
-            if (cn > remaining || s == 3) cn = remaining;
-            p.head_cb[s] = cb;
-            p.head_cn[s] = cn;
-            cb += cn;
-            remaining -= cn;
-        }
-    }
     p.a_mode = A_LINEAR;
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
