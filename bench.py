@@ -499,7 +499,8 @@ def torch_cuda_reference(cfg, sd, dev_in, dt, steps, dev):
 def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
     """images/s of one optimisation step through the public API: model.train() under autocast, ComputeLoss, GradScaler-scaled
     backward, fused un-scale + clip + SGD-Nesterov (3 groups) + zero_grad (+ ModelEMA on rank 0, as train.py:251 does); per-GPU
-    batch fixed, gradients all-reduced by DDP for N > 1 (reference train.py:401-421, utils/torch_utils.py:61-70)."""
+    batch fixed, gradients averaged over ranks for N > 1 by FusedSGD.data_parallel -- one NCCL all-reduce of the packed arena -- with the
+    smart_DDP wrapper timed beside it (reference train.py:401-421, utils/torch_utils.py:61-70)."""
     import torch.distributed as dist
 
     from oracle import loss_ref, model_ref  # synthetic labels / weights, and the torch reference arm
@@ -525,8 +526,10 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
 
     model = build()
     loss_fn = ComputeLoss(model)
-    net = smart_DDP(model) if world > 1 else model
+    net = model
     opt = smart_optimizer(model, "SGD", lr=1e-3, momentum=hyp["momentum"], decay=hyp["weight_decay"])
+    if world > 1:  # the path's collective: gradients packed into one arena, ONE NCCL all-reduce per step, update from the arena
+        opt.data_parallel(model)
     scaler = torch.amp.GradScaler("cuda", enabled=tdt == torch.float16)
     ema = ModelEMA(model) if rank == 0 else None
     n_rot = 3
@@ -535,16 +538,16 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
     dev_img = [h.to(dev) for h in host_img]
     dev_tgt = [h.to(dev) for h in host_tgt]
 
-    def step(img, tgt, sync=True):
+    def step(img, tgt, net=net, opt=opt, loss_fn=loss_fn, scaler=scaler, ema=ema, model=model, sync=True):
         import contextlib
 
-        ctx = net.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+        ctx = net.no_sync() if (net is not model and not sync) else contextlib.nullcontext()
         with ctx:
             with torch.autocast("cuda", dtype=tdt):
                 p = net(img)
             loss, items = loss_fn(p, tgt)
             if world > 1:
-                loss = loss * world  # train.py:405: DDP averages gradients, the reference rescales
+                loss = loss * world  # train.py:405: gradients are averaged over ranks, the reference rescales
             scaler.scale(loss).backward()
         opt.fused_step(scaler=scaler, max_norm=10.0, ema=ema, model=model)  # train.py:413-421
         opt.zero_grad()
@@ -575,17 +578,40 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
         e1.record()
         D.barrier()
         _, ar_ms = aggregate_throughput(0, e0.elapsed_time(e1) / 10, dev)
+        # the same step with the all-reduce skipped (pack + update from the arena still run): what the collective exposes
+        dp = opt._dp
+        opt._dp = (dp[0], 1)
+        step(dev_img[0], dev_tgt[0])
+        ms_local = timed(D, lambda i: step(dev_img[i % n_rot], dev_tgt[i % n_rot]), steps)
+        opt._dp = dp
+        _, local_ms = aggregate_throughput(0, ms_local, dev)
+        # and the reference's arrangement for comparison: the module wrapped by smart_DDP (torch DistributedDataParallel:
+        # autograd hooks, 25 MB buckets, per-step buffer broadcast), same kernels and optimizer otherwise
+        ddp_ms = None
         try:
-            ms_nosync = timed(D, lambda i: step(dev_img[i % n_rot], dev_tgt[i % n_rot], sync=False), steps)
-        except Exception:  # noqa: BLE001  (a DDP build that refuses no_sync with static_graph)
-            ms_nosync = float("nan")
-        _, nosync_ms = aggregate_throughput(0, ms_nosync, dev)
+            m2 = build()
+            net2 = smart_DDP(m2)
+            opt2 = smart_optimizer(m2, "SGD", lr=1e-3, momentum=hyp["momentum"], decay=hyp["weight_decay"])
+            sc2 = torch.amp.GradScaler("cuda", enabled=tdt == torch.float16)
+            kw = dict(net=net2, opt=opt2, loss_fn=ComputeLoss(m2), scaler=sc2, ema=None, model=m2)
+            for i in range(3):
+                step(dev_img[i % n_rot], dev_tgt[i % n_rot], **kw)
+            ms_ddp = timed(D, lambda i: step(dev_img[i % n_rot], dev_tgt[i % n_rot], **kw), steps)
+            _, ddp_worst = aggregate_throughput(0, ms_ddp, dev)
+            ddp_ms = ddp_worst / steps
+            del m2, net2, opt2, kw
+        except Exception as ex:  # noqa: BLE001
+            ddp_ms = repr(ex)[:200]
         nbytes = 4 * n_params
-        comm = {"collective": "NCCL all-reduce of the fp32 gradients (DDP buckets, overlapped with backward)", "bytes_per_step": nbytes,
-                "allreduce_ms_in_isolation": ar_ms, "bus_gbs_in_isolation": 2 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9,
-                "step_ms_with_allreduce": worst_ms / steps, "step_ms_without_allreduce (no_sync)": nosync_ms / steps,
-                "exposed_ms_per_step": (max(worst_ms - nosync_ms, 0.0) / steps) if nosync_ms == nosync_ms else None,
-                "what_limits": "per-GPU step time (kernels + Python launch issue); the all-reduce is hidden behind backward except its tail"}
+        comm = {"collective": "ONE NCCL all-reduce (average) per step over the packed fp32 gradient arena (FusedSGD.data_parallel: y5_grad_pack -> "
+                              "all_reduce -> y5_opt_step reading the arena); no autograd hooks / buckets / copy-backs",
+                "bytes_per_step": nbytes, "allreduce_ms_in_isolation": ar_ms,
+                "bus_gbs_in_isolation": 2 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9,
+                "step_ms_with_allreduce": worst_ms / steps, "step_ms_without_allreduce": local_ms / steps,
+                "exposed_ms_per_step": max(worst_ms - local_ms, 0.0) / steps,
+                "step_ms_torch_DDP_wrapper (smart_DDP, same kernels)": ddp_ms,
+                "what_limits": "per-GPU step time (kernels + Python launch issue); the all-reduce is not overlapped -- it is one "
+                               "call of ~allreduce_ms_in_isolation after backward"}
         del flat
 
     # e2e: pinned host uint8 images + labels uploaded every step, loss items read back every step
@@ -690,7 +716,7 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
                "cuda_graph_step": graphed, "torch_cuda_reference_train": tc_ref,
                "detail": {"model": model_name, "per_gpu_batch": bs, "global_batch": bs * world, "params": n_params,
                           "recipe": f"autocast {dt}, GradScaler, fp32 master weights, fused un-scale/clip/SGD-Nesterov(3 groups)/zero_grad, ModelEMA on rank 0",
-                          "parallelism": f"dp{world} (DDP gradient all-reduce over NCCL)" if world > 1 else "single GPU",
+                          "parallelism": f"dp{world} (one NCCL all-reduce of the packed gradient arena per step)" if world > 1 else "single GPU",
                           "labels": "COCO128-shaped synthetic targets (oracle.loss_ref.synth_targets), ~7.3 per image"}}
     del model, net, opt
     torch.cuda.empty_cache()

@@ -374,6 +374,18 @@ int32_t y5_opt_chunk_elems(void);
 int y5_opt_step(const y5_opt_tensor* table, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
                 float* hyper, float* partial, int32_t do_step, int32_t do_ema, int32_t zero_grad, void* stream);
 
+/* Data-parallel gradient exchange, device half (utils/torch_utils.py:61-70 smart_DDP / train.py:404-414): copy every gradient
+ * of `table` (entries with mom != NULL; a NULL grad contributes zeros) into ONE contiguous fp32 arena in a single launch, so the
+ * all-reduce is one NCCL call over the arena and y5_opt_step reads the averaged gradients from it (a second table whose grad
+ * pointers are arena + arena_offset[t]).  arena_offset[t]: element offset of tensor t, a multiple of 4; arena 16-byte aligned.
+ * present[t] = 1.0 / 0.0: tensor t had a gradient on this rank (callers place `present` right behind the arena so the same
+ * all-reduce averages it); y5_grad_bind then rewrites the arena table's gradient pointers -- NULL where present[t] == 0 on every
+ * rank -- so the update skips such parameters like the single-process step does. */
+int y5_grad_pack(const y5_opt_tensor* table, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                 const int64_t* arena_offset, float* arena, float* present, void* stream);
+int y5_grad_bind(y5_opt_tensor* arena_table, int32_t n_tensors, const int64_t* arena_offset, float* arena, const float* present,
+                 void* stream);
+
 /* Fold eval-mode BatchNorm into a conv and pack it for y5_conv_bn_silu_fwd in ONE launch (utils/torch_utils.py:224-254):
  *   packed[o][r][s][i_pad] = w[o][i][r][s] * gamma[o] / sqrt(var[o] + eps)   (activation dtype, zero padded)
  *   bias_out[o]            = beta[o] + (conv_bias[o] - mean[o]) * gamma[o] / sqrt(var[o] + eps)   (fp32)

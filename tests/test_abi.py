@@ -69,6 +69,8 @@ def test_pre_post_optimizer_argument_validation_without_gpu(built_lib):
     assert lib.y5_match_batch(4096, 1800, 6, None, 2, 5000, None, 0, 4096, 10, 1e-7, 4096, None) == -2  # max_det cap
     assert lib.y5_scale_boxes(None, 6, 10, None, 0, None, None, None) == -1
     assert lib.y5_opt_chunk_elems() > 0 and lib.y5_opt_step(None, None, None, 4, None, None, 1, 1, 1, None) == -1
+    assert lib.y5_grad_pack(None, None, None, 4, None, None, None, None) == -1 and lib.y5_grad_pack(None, None, None, 0, None, None, None, None) == 0
+    assert lib.y5_grad_bind(None, 4, None, None, None, None) == -1 and lib.y5_grad_bind(None, 0, None, None, None, None) == 0
     assert lib.y5_fold_pack(None, _lib.Y5_F32, 8, 8, 1, 1, None, None, None, None, None, _lib.Y5_F32, 1e-3, None, 8, 8, None, _lib.Y5_F16, None) == -1
     assert lib.y5_loss_fwd_bwd_scaled(None, None, None, None, None, None, None, None, 0, None) == -1
 

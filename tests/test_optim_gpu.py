@@ -226,3 +226,45 @@ def test_graphed_train_step_with_loss_scaling_ema_and_schedule(cuda):
             assert float((ema_a - w0).norm()) > 0 and float((ema_a - ema_b).norm()) <= 0.05 * float((ema_b - w0).norm())
     assert ea.updates == eb.updates == 3 and float(step.scaler.get_scale()) == float(sb.get_scale())
     assert int(ma.model[0].bn.num_batches_tracked) == 3 and all(bool(torch.isfinite(v).all()) for v in ma.parameters())
+
+
+def test_data_parallel_mode_world1_packs_gradients_and_steps_identically(cuda):
+    """FusedSGD.data_parallel (the device half of the gradient exchange, y5_grad_pack): in a 1-rank group the arena must hold
+    every gradient bit-exactly at its 16-byte aligned offset, and the step taken from the arena must equal the plain step."""
+    import torch.distributed as dist
+
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29683", rank=0, world_size=1, device_id=cuda)
+    try:
+        torch.manual_seed(5)
+        shapes = [(33, 7, 3, 3), (33,), (1,), (64, 33, 1, 1), (5,), (70001,)]
+        ma = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes])
+        mb = torch.nn.ParameterList([torch.nn.Parameter(p.detach().clone()) for p in ma])
+        oa = FusedSGD(list(ma), lr=0.05, momentum=0.9, weight_decay=1e-3, nesterov=True)
+        ob = FusedSGD(list(mb), lr=0.05, momentum=0.9, weight_decay=1e-3, nesterov=True)
+        oa.data_parallel(ma)
+        for it in range(3):
+            for i, (pa, pb) in enumerate(zip(ma, mb)):
+                g = torch.randn_like(pa) * (10.0 if it == 1 else 1.0)
+                if i == 4 and it == 2:
+                    pa.grad = pb.grad = None  # a parameter without a gradient this step: zeros in the arena, no update
+                    continue
+                pa.grad, pb.grad = g, g.clone()
+            grads = [None if p.grad is None else p.grad.clone() for p in ma]
+            oa.fused_step(max_norm=10.0)
+            ob.fused_step(max_norm=10.0)
+            off = 0
+            for p, g in zip(ma, grads):
+                n = p.numel()
+                want = torch.zeros(n, device=cuda) if g is None else g.flatten()
+                assert torch.equal(oa._arena[off : off + n], want)
+                off += (n + 3) // 4 * 4
+            for pa, pb in zip(ma, mb):
+                assert torch.equal(pa, pb)
+            assert oa.last_grad_norm == ob.last_grad_norm
+            oa.zero_grad()
+            ob.zero_grad()
+    finally:
+        if own_group:
+            dist.destroy_process_group()

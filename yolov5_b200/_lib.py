@@ -155,6 +155,8 @@ SIGNATURES = {
     "y5_match_batch": (_I32, [_P, _I64, _I32, _P, _I32, _I32, _P, _I32, _P, _I32, _F, _P, _P]),
     "y5_opt_chunk_elems": (_I32, []),
     "y5_opt_step": (_I32, [_P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _P]),
+    "y5_grad_pack": (_I32, [_P, _P, _P, _I32, _P, _P, _P, _P]),
+    "y5_grad_bind": (_I32, [_P, _I32, _P, _P, _P, _P]),
     "y5_fold_pack": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _I32, _I32, _P, _I32, _P]),
 }
 

@@ -68,13 +68,24 @@ CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
 }
 CUtensorMapDataType tm_dtype(int dtype) { return dtype == Y5_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
 
+// L2 promotion (the granularity at which a TMA read pulls its neighbourhood into L2): 256 B helps when the bytes next to a box
+// are read soon after (the next channel chunk of the same pixels, the next pixel of a dense tensor); on a channel SLICE of a
+// wider tensor (a C3 branch reading one half of the stacked cv1|cv2 output: 128 B out of every 256 B) it doubles the DRAM reads
+// (ncu, yolov5l model.2.m*.cv1: 417 MB read for a 210 MB operand).  -> never promote beyond the slice's own contiguous bytes.
+static CUtensorMapL2promotion promotion_for(unsigned long long row_bytes, unsigned long long pitch_bytes) {
+    if (row_bytes == pitch_bytes || row_bytes >= 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (row_bytes >= 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (row_bytes >= 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 int encode_tiled(CUtensorMap* map, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                  const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
     auto fn = driver_fn_encode_tiled();
     if (!fn) return set_error(Y5_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, tm_dtype(dtype), rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    sw, promotion_for(dims[0] * 2, rank > 1 ? strides_bytes[0] : dims[0] * 2), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(Y5_E_DRIVER, "cuTensorMapEncodeTiled(%s) failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u stride0 %llu",
                          what, int(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
@@ -96,7 +107,8 @@ int encode_im2col(CUtensorMap* map, int dtype, const void* base, int C, int W, i
     int upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(map, tm_dtype(dtype), 4, const_cast<void*>(base), dims, strides, lower, upper, channels_per_pixel, pixels_per_column,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promotion_for((unsigned long long)C * 2, (unsigned long long)xs * 2),
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(Y5_E_DRIVER, "cuTensorMapEncodeIm2col failed (%d): C %d W %d H %d N %d k %dx%d s %d p %d,%d", int(r), C, W, H, N,
                          kh, kw, stride, pad_h, pad_w);

@@ -169,6 +169,30 @@ class FusedSGD(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov))
         self._tab = None
         self._tab_key = None
+        self._dp = None  # (process group, world size) once data_parallel() was called
+
+    # ------------------------------------------------------------------ data parallel
+    def data_parallel(self, model, process_group=None, src: int = 0):
+        """Turn the step into the data-parallel one (what reference train.py gets from smart_DDP, utils/torch_utils.py:61-70):
+        parameters and buffers are broadcast from rank `src` once; from then on `fused_step` copies every gradient into one
+        contiguous fp32 arena (y5_grad_pack, one launch), all-reduces the arena with ONE NCCL call (average over ranks, like
+        DDP) and updates from the averaged arena.  No autograd hooks, buckets or copy-backs, and nothing but the all-reduce
+        itself touches the link.  `model` must be the plain module (not wrapped in DistributedDataParallel); gradient
+        accumulation needs no `no_sync()`: ranks only talk inside `fused_step`.  BatchNorm statistics stay per rank (the
+        reference does not use SyncBatchNorm unless asked)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("y5b200: FusedSGD.data_parallel needs an initialised torch.distributed process group")
+        if isinstance(model, (nn.parallel.DataParallel, nn.parallel.DistributedDataParallel)):
+            raise TypeError("y5b200: pass the plain module to FusedSGD.data_parallel (DistributedDataParallel would all-reduce a second time)")
+        world = dist.get_world_size(process_group)
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=dist.get_global_rank(process_group, src) if process_group is not None else src, group=process_group)
+        self._dp = (process_group, world)
+        self._tab = None  # rebuild the tables with the arena
+        return self
 
     # ------------------------------------------------------------------ tables
     def _params(self):
@@ -201,6 +225,23 @@ class FusedSGD(torch.optim.Optimizer):
             if m_t.data_ptr() not in seen:
                 entries.append((m_t.detach(), None, e_t, 0))
         self._tab = _OptTable(entries, dev)
+        self._tab_arena = None
+        if self._dp is not None:
+            # data-parallel mode: the gradients' home for the all-reduce and the update.  Tensor t sits at a 16-byte aligned
+            # offset; the second table is the first with its gradient column pointing into the arena (fixed addresses).
+            offs, o = [], 0
+            for e in entries:
+                offs.append(o if e[1] is not None else 0)
+                if e[1] is not None:
+                    o += (e[0].numel() + 3) // 4 * 4
+            # [gradients | one "had a gradient on this rank" float per table entry]: one buffer, one all-reduce
+            self._arena_all = torch.zeros(max(o, 4) + len(entries), dtype=torch.float32, device=dev)
+            self._arena = self._arena_all[: max(o, 4)]
+            self._present = self._arena_all[max(o, 4) :]
+            self._arena_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+            self._tab_arena = _OptTable(entries, dev)
+            self._tab_arena.set_grads([self._arena.data_ptr() + 4 * off if e[1] is not None else 0 for e, off in zip(entries, offs)])
+            self._tab_arena.upload()
         self._tab_key = key
         self._plist = [p for _, p in ps]
         self._flat_m = flat_m
@@ -250,6 +291,19 @@ class FusedSGD(torch.optim.Optimizer):
         use_scaler = scaler is not None and scaler.is_enabled() and getattr(scaler, "_scale", None) is not None
         if use_scaler:
             torch.reciprocal(scaler._scale.reshape(1).float(), out=self._hyper[_lib.OPT_INV_SCALE : _lib.OPT_INV_SCALE + 1])
+        if self._dp is not None:
+            import torch.distributed as dist
+
+            with _lib.on(dev):
+                _lib.check(_lib.lib().y5_grad_pack(t.table.data_ptr(), t.chunk_tensor.data_ptr(), t.chunk_index.data_ptr(), t.n_chunks,
+                                                   self._arena_off.data_ptr(), self._arena.data_ptr(), self._present.data_ptr(),
+                                                   C.c_void_p(_lib.stream_ptr(dev))), "grad_pack")
+            if self._dp[1] > 1:
+                dist.all_reduce(self._arena_all, op=dist.ReduceOp.AVG, group=self._dp[0])
+            t = self._tab_arena
+            with _lib.on(dev):
+                _lib.check(_lib.lib().y5_grad_bind(t.table.data_ptr(), len(t.keep), self._arena_off.data_ptr(), self._arena.data_ptr(),
+                                                   self._present.data_ptr(), C.c_void_p(_lib.stream_ptr(dev))), "grad_bind")
         with _lib.on(dev):
             _lib.check(_lib.lib().y5_opt_step(t.table.data_ptr(), t.chunk_tensor.data_ptr(), t.chunk_index.data_ptr(), t.n_chunks,
                                               self._hyper.data_ptr(), t.partial.data_ptr(), 1, 1 if ema is not None else 0, 0,
