@@ -81,8 +81,12 @@ typedef struct y5_conv_desc {
     int64_t in_y_stride;  /* elements between rows   (0 = in_w * in_x_stride) */
     int64_t in_n_stride;  /* elements between images (0 = in_h * in_y_stride) */
     int32_t a_mode;       /* activation fetch: 0 auto, 1 force TMA-im2col, 2 force shifted-patch (stride-1 only) */
-    int32_t reserved;     /* tuning/tests, only read with a forced block_n >= 128: bit 1 = 256-row tiles (two 128-row
-                             sub-tiles per B tile); bits 8.. = thread-block cluster size (2|4) for weight-tile multicast */
+    int32_t reserved;     /* flags.  bit 6 (64): the weights are constant -- not written by whatever precedes this launch in the
+                             stream -- so the kernel may fetch them before its programmatic-dependency wait (inference programs
+                             set it; a training forward that packs weights right before the conv must not).  Tuning / tests:
+                             bit 4 (16) row-strided stores instead of the TMA-store epilogue, bit 5 (32) one patch copy per
+                             horizontal tap instead of the wide patch; with a forced block_n >= 128 also bit 1 (2) = 256-row
+                             tiles, bit 2 (4) = CTA pairs, bits 8.. = cluster size (2|4) for weight-tile multicast */
 } y5_conv_desc;
 
 /* Tiling the library will use for a conv: block_k decides the weight packing (cin_pad = ceil(in_c/block_k)*block_k). */

@@ -55,6 +55,31 @@ def test_conv_3x3_both_fetch_modes(cuda, case, a_mode):
     assert untouched
 
 
+@pytest.mark.parametrize("narrow", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case,kw", [
+    ((2, 32, 32, 64, 64, 3, 1, 1), dict()),                          # 64 -> 64: two sub-tiles side by side in one 24-pixel-wide patch
+    ((2, 40, 40, 64, 64, 3, 1, 1), dict()),                          # odd number of 8-pixel tiles per row: sub-tiles cannot share a patch
+    ((1, 48, 80, 128, 128, 3, 1, 1), dict()),                        # two channel chunks, 128-wide N tile
+    ((2, 13, 27, 64, 32, 3, 1, 1), dict()),                          # partial tiles in x and y
+    ((1, 9, 130, 64, 96, 3, 1, 1), dict()),                          # wide and flat
+    ((2, 24, 24, 192, 64, 5, 1, 2), dict()),                         # 5x5, three channel chunks (odd tiles per row -> narrow mode)
+    ((4, 40, 40, 64, 256, 3, 1, 1), dict(block_n=256, cg2=True)),    # CTA pairs
+    ((4, 32, 32, 128, 128, 3, 1, 1), dict(block_n=128, cg2=True, mt2=True)),  # CTA pairs, two sub-tiles per CTA
+    ((4, 32, 32, 64, 64, 3, 1, 1), dict(block_n=64, cg2=True)),      # 64-wide CTA pairs (256 x 64 MMAs), shared 24-pixel patch
+    ((3, 40, 40, 128, 64, 3, 1, 1), dict(block_n=64, cg2=True)),     # same, odd tile count per row (separate patches), M tail pair
+    ((2, 24, 24, 192, 128, 5, 1, 2), dict()),                        # 5x5 in wide mode (single sub-tile)
+])
+def test_conv_wide_patch(cuda, case, kw, dtype, narrow):
+    """Stride-1 k x k convs with 64-channel chunks fetch ONE (16+k-1) x PW patch per chunk and read all k*k taps from it through
+    descriptor offsets + the swizzle base offset (`narrow=False`); the one-copy-per-horizontal-tap mode (`narrow=True`, reserved bit
+    32) must give the same answer.  Residual + channel-slice views on both sides."""
+    got, ref, untouched = conv_case(cuda, dtype, *case, a_mode=2, residual=True, in_extra=8, out_extra=24, narrow_patch=narrow, wide_patch=not narrow,
+                                     **kw)
+    assert rel_err(got, ref) < TOL[dtype], (case, kw, narrow, rel_err(got, ref))
+    assert untouched
+
+
 def test_conv_no_activation(cuda):
     got, ref, _ = conv_case(cuda, torch.float16, 2, 16, 16, 64, 64, 1, 1, 0, act=False)
     assert rel_err(got, ref) < 2e-3

@@ -10,6 +10,13 @@
 //           horizontal tap s, ONE copy brings the (th+kh-1) x tw input patch; the kh vertical taps are the same smem
 //           patch read at row offsets r*tw (a plain descriptor offset, still 1024-B aligned because tw % 8 == 0).
 //           L2->smem traffic for A drops from kh*kw to kw*(th+kh-1)/th reads per input element.
+//   PATCH, wide (64-channel chunks = 128-byte rows, kw > 1): tile = 16 rows x 8 pixels, ONE copy per channel chunk brings the
+//           (16+kh-1) x PW patch (PW = 8*MT + 8 pixels: the MT sub-tiles sit side by side in it) and ALL kh*kw taps are read
+//           from it: tap (r, s) = descriptor start + (r*PW + s) rows, the 8 pixels of an output row are one 8-row swizzle
+//           group, consecutive output rows are PW*128 bytes apart (the descriptor's group stride).  The start is then s rows off the
+//           1024-byte swizzle pattern; the descriptor's base-offset field must stay 0 for that (measured on B200: the hardware
+//           swizzles on absolute shared-memory address bits, like the TMA write did; a non-zero base offset shifts the pattern twice).
+//           A traffic: (16+kh-1)*PW / (128*MT) reads per input element = 2.25 (MT 1) / 1.69 (MT 2) instead of 3.75.
 // Weights (B): 2-D TMA tiles of the packed [Cout][kh][kw][Cin_pad] matrix, one per (tap, channel chunk); A and B
 // have separate mbarrier rings because one A patch feeds kh B tiles.
 // MMA: one elected thread issues tcgen05.mma (M128 x BLOCK_N x K16, fp32 accumulate) into one of two TMEM
@@ -64,11 +71,16 @@ struct ConvParams {
     int a_mode;
     int Ho, Wo, HoWo, stride, pad_h, pad_w;
     int tw, th, tiles_x, tiles_y;  // PATCH: spatial sub-tile th x tw (= 128 pixels), sub-tiles per image
+    int b_grouped;              // PATCH: a weight stage holds all kh tiles of one (chunk, horizontal tap) group: one barrier round per group
+    uint32_t b_sub_bytes;       // bytes of one weight tile inside a (possibly grouped) stage
+    int cluster_n;              // thread-block cluster size of the launch (what %cluster_nctarank returns; read from here in the hot loops)
+    int patch_pw;               // > 0: wide patch mode, patch row pitch in pixels (8*MT + 8); one A copy per channel chunk feeds kh*kw taps
     float rcp_per_img, rcp_tiles_x, rcp_HoWo, rcp_Wo;  // reciprocals for fdiv(): exact small-integer division in ~7 instructions
     int a_stages, b_stages;
     int tma_store;              // epilogue: per-warp swizzled smem staging + cp.async.bulk.tensor store instead of row-strided STG
     int c_bw, c_bh;             // PATCH + tma_store: store box = c_bw pixels x c_bh rows (c_bw * c_bh = 32)
-    int b_resident;             // weights of the (single) N tile stay in shared memory for the whole kernel: loaded with the first tile only
+    int b_resident;             // weights of the (single) N tile stay in shared memory for the whole kernel: 1 = loaded with the first tile,
+                                // 2 = constant weights, fetched BEFORE the programmatic-dependency wait (overlaps the previous kernel's tail)
     uint32_t a_sub_bytes, a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
     int is_bf16, act;
@@ -189,6 +201,73 @@ __device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float*
     }
 }
 
+// The MMA-issuing warp's loop, specialised.  ncu (yolov5l, 64-channel 3x3 layer): this warp never waits on a barrier, it is busy
+// for the whole kernel executing ~120 SASS instructions per 8 MMAs at ~9 clocks each (uniform-datapath latencies, one warp), i.e.
+// ITS instruction count bounds every layer whose MMAs are short (N <= 128, or few K steps per barrier round).  Every run-time
+// mode test inside the loop costs a constant load + compare + branch per weight tile, so the common case -- 64-channel chunks
+// (4 K steps), streamed weights, no weight multicast, no wide patch -- gets its own straight-line loops here, chosen once per
+// kernel; the generic loop in the kernel body handles the rest.
+//   PATCH   : A groups of kh weight tiles (vertical taps read the same activation patch at row offsets)
+//   GROUPED : the kh tiles of a group share one weight stage (one barrier round and one commit per group)
+template <int BLOCK_N, int MT, int CG, bool PATCH, bool GROUPED>
+__device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
+                                               int tile0, int tile_step, int num_tiles) {
+    constexpr int kAccCols = MT * BLOCK_N;
+    constexpr int NACC = kAccCols <= 256 ? 2 : 1;
+    const uint32_t dhi = umma_desc_hi(128);
+    const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4, a_sub16 = p.a_sub_bytes >> 4, b_sub16 = p.b_sub_bytes >> 4;
+    const uint32_t a_shift16 = PATCH ? static_cast<uint32_t>(p.tw * 128) >> 4 : 0u;
+    const uint32_t idesc = p.idesc;
+    const int a_stages = p.a_stages, b_stages = p.b_stages;
+    const int grp = PATCH ? p.kh : 1;
+    const int num_groups = PATCH ? p.c_chunks * p.kw : p.kh * p.kw * p.c_chunks;
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        uint32_t accum = 0;
+        for (int g = 0; g < num_groups; ++g) {
+            mbar_wait(&a_full[as], aph);
+            uint32_t a_lo = a_base + as * a_stage16;
+            const bool last_group = g == num_groups - 1;
+            for (int j = 0; j < grp; ++j) {
+                const bool stage_first = !GROUPED || j == 0, stage_last = !GROUPED || j == grp - 1;
+                if (stage_first) mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                const uint32_t b_lo = b_base + bs * b_stage16 + (GROUPED ? j * b_sub16 : 0u);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int mi = 0; mi < MT; ++mi) {
+                            if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                            else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                        }
+                    }
+                    if (CG == 2) {
+                        if (stage_last) umma_commit_cg2(&b_empty[bs], 3);
+                        if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
+                        if (j == grp - 1 && last_group) umma_commit_cg2(&tmem_full[acc], 3);
+                    } else {
+                        if (stage_last) umma_commit(&b_empty[bs]);
+                        if (j == grp - 1) umma_commit(&a_empty[as]);
+                        if (j == grp - 1 && last_group) umma_commit(&tmem_full[acc]);
+                    }
+                }
+                __syncwarp();
+                accum = 1;
+                if (stage_last && ++bs == b_stages) { bs = 0; bph ^= 1; }
+                a_lo += a_shift16;
+            }
+            if (++as == a_stages) { as = 0; aph ^= 1; }
+        }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+    }
+}
+
 // CG = 2: CTA-pair mode (tcgen05 cta_group::2).  The two CTAs of a cluster work on two M super-tiles of the SAME N tile as ONE
 // M = 256 MMA: each CTA stages its own 128 activation rows and HALF of the weight tile (BLOCK_N / 2 rows), the leader's MMA
 // reads both CTAs' shared memory and writes 128 x BLOCK_N accumulators into each CTA's TMEM.  Weight traffic L2 -> smem per
@@ -200,7 +279,7 @@ template <int BLOCK_N, int EPI, int MT, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                  const ConvParams p) {
-    static_assert(CG == 1 || (EPI == 0 && BLOCK_N >= 128), "CTA pairs: plain epilogue, N tile >= 128");
+    static_assert(CG == 1 || (EPI == 0 && BLOCK_N >= 64), "CTA pairs: plain epilogue, N tile >= 64");
     constexpr int kAccCols = MT * BLOCK_N;          // TMEM columns per accumulator set (128, 256 or 512)
     constexpr int NACC = kAccCols <= 256 ? 2 : 1;   // two sets when they fit: epilogue of tile i overlaps the MMAs of tile i+1
     constexpr uint32_t kTmemCols = NACC * kAccCols < 32 ? 32 : NACC * kAccCols;
@@ -259,6 +338,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, bias preload of constant weights) may
     // overlap the tail of the previous kernel in the stream; activations are only touched after this point.
+    if (warp == 0 && p.b_resident == 2) {  // the weights do not depend on the previous kernel: start fetching them now
+        const int num_kb = p.kh * p.kw * p.c_chunks;
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_arrive_expect_tx(&b_full[kb], p.b_stage_bytes);
+                tma_load_2d(&tmB, &b_full[kb], sB + kb * p.b_stage_bytes, kb * p.block_k, 0);
+            }
+        }
+        __syncwarp();
+    }
     griddep_wait();
     griddep_launch_dependents();
 
@@ -280,8 +369,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // K iteration: "A groups" each feeding `grp` consecutive B tiles.
     //   PATCH : groups = (chunk cc, horizontal tap s), members r = 0..kh-1   -> k-block (r*kw + s)*c_chunks + cc
     //   else  : groups = k-blocks in (r, s, cc) order, one member each
-    const int grp = patch ? p.kh : 1;
-    const int num_groups = patch ? p.c_chunks * p.kw : p.kh * p.kw * p.c_chunks;
+    //   PATCH wide: groups = channel chunks cc, members (r, s) in weight order   -> k-block (r*kw + s)*c_chunks + cc
+    const bool wide = p.patch_pw > 0;
+    const int grp = wide ? p.kh * p.kw : (patch ? p.kh : 1);
+    const int num_groups = wide ? p.c_chunks : (patch ? p.c_chunks * p.kw : p.kh * p.kw * p.c_chunks);
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -325,7 +416,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int mi = 0; mi < MT; ++mi) {
                             uint8_t* a_dst = sA + as * p.a_stage_bytes + mi * p.a_sub_bytes;
-                            if (CG == 2) {
+                            if (wide) {  // one patch for all sub-tiles and taps (sub-tile mi starts 8 pixels = 1024 bytes into it)
+                                if (mi == 0) {
+                                    if (CG == 2) tma_load_4d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, x0[0], y0[0], img[0]);
+                                    else tma_load_4d(&tmA, &a_full[as], a_dst, cc * p.block_k, x0[0], y0[0], img[0]);
+                                }
+                            } else if (CG == 2) {
                                 if (p.a_mode == A_LINEAR) tma_load_2d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, (ms * MT + mi) * kBlockM);
                                 else if (p.a_mode == A_IM2COL)
                                     tma_load_im2col_4d_cg2(&tmA, a_bar, a_dst, cc * p.block_k, x0[mi], y0[mi], img[mi],
@@ -342,33 +438,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
                     for (int j = 0; j < grp; ++j) {
                         const int r = patch ? j : r0;
-                        const int kb = (r * p.kw + s) * p.c_chunks + cc;
+                        const int kb = wide ? j * p.c_chunks + cc : (r * p.kw + s) * p.c_chunks + cc;
                         if (p.b_resident) {  // slot kb holds k-block kb for every tile of this CTA (single N tile)
-                            if (tile == tile0 && elect_one()) {
+                            if (p.b_resident == 1 && tile == tile0 && elect_one()) {
                                 mbar_arrive_expect_tx(&b_full[kb], p.b_stage_bytes);
                                 tma_load_2d(&tmB, &b_full[kb], sB + kb * p.b_stage_bytes, kb * p.block_k, n0);
                             }
                             __syncwarp();
                             continue;
                         }
-                        mbar_wait(&b_empty[bs], bph ^ 1);
+                        // grouped stages: the kh tiles of this group share one stage (one wait, one expect_tx covering all of them)
+                        const bool stage_first = !p.b_grouped || j == 0, stage_last = !p.b_grouped || j == grp - 1;
+                        if (stage_first) mbar_wait(&b_empty[bs], bph ^ 1);
                         if (elect_one()) {
-                            if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&b_full[bs], CG * p.b_stage_bytes);
+                            if (stage_first && (CG == 1 || crank == 0)) mbar_arrive_expect_tx(&b_full[bs], CG * p.b_stage_bytes);
+                            uint8_t* b_dst = sB + bs * p.b_stage_bytes + (p.b_grouped ? j * p.b_sub_bytes : 0u);
                             if (CG == 2)  // my half of the weight tile's rows, into my own shared memory; bytes counted by the leader
-                                tma_load_2d_cg2(&tmB, mapa_u32(&b_full[bs], 0), sB + bs * p.b_stage_bytes, kb * p.block_k,
-                                                n0 + static_cast<int>(crank) * (BLOCK_N / 2));
-                            else if (csize == 1) tma_load_2d(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes, kb * p.block_k, n0);
+                                tma_load_2d_cg2(&tmB, mapa_u32(&b_full[bs], 0), b_dst, kb * p.block_k, n0 + static_cast<int>(crank) * (BLOCK_N / 2));
+                            else if (csize == 1) tma_load_2d(&tmB, &b_full[bs], b_dst, kb * p.block_k, n0);
                             else {  // my slice of the rows, delivered to every CTA of the cluster
                                 const uint32_t slice_rows = BLOCK_N / csize;
-                                tma_load_2d_mcast(&tmB, &b_full[bs], sB + bs * p.b_stage_bytes + crank * slice_rows * row_bytes,
-                                                  kb * p.block_k, n0 + crank * slice_rows, cmask);
+                                tma_load_2d_mcast(&tmB, &b_full[bs], b_dst + crank * slice_rows * row_bytes, kb * p.block_k, n0 + crank * slice_rows,
+                                                  cmask);
                             }
                         }
                         __syncwarp();
-                        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        if (stage_last && ++bs == p.b_stages) { bs = 0; bph ^= 1; }
                     }
                 };
-                if (patch) {
+                if (wide) {
+                    for (int cc = 0; cc < p.c_chunks; ++cc) issue_group(cc, 0, 0);
+                } else if (patch) {
                     for (int cc = 0; cc < p.c_chunks; ++cc)
                         for (int s = 0; s < p.kw; ++s) issue_group(cc, s, 0);
                 } else {
@@ -380,7 +480,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (CG == 1 || crank == 0) {   // pair mode: the leader CTA issues for both.  whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
+        const bool lean = EPI == 0 && p.block_k == 64 && !p.b_resident && !wide && p.cluster_n == CG;
+        if ((CG == 1 || crank == 0) && lean) {   // the common case: specialised straight-line loops (see mma_issue_lean)
+            const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
+            if (!patch)
+                mma_issue_lean<BLOCK_N, MT, CG, false, false>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
+                                                              tile_step, num_tiles);
+            else if (p.b_grouped)
+                mma_issue_lean<BLOCK_N, MT, CG, true, true>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
+                                                            tile_step, num_tiles);
+            else
+                mma_issue_lean<BLOCK_N, MT, CG, true, false>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
+                                                             tile_step, num_tiles);
+        } else if (CG == 1 || crank == 0) {   // pair mode: the leader CTA issues for both.  whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase = 0;
             const int k_steps = p.block_k / 16;
@@ -388,7 +500,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t dhi = umma_desc_hi(row_bytes);
             const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
             const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4, a_sub16 = p.a_sub_bytes >> 4;
+            const uint32_t b_sub16 = p.b_sub_bytes >> 4;
             const uint32_t a_shift16 = patch ? (p.tw * row_bytes) >> 4 : 0;  // between vertical taps inside a patch
+            // wide patch: group stride = one patch row (PW pixels); the tap's horizontal offset s goes into the swizzle base offset
+            const uint32_t dhi_wide = (dhi & ~0x3FFFu) | (((static_cast<uint32_t>(p.patch_pw) * row_bytes) >> 4) & 0x3FFFu);
+            const uint32_t row16 = row_bytes >> 4;
             const uint32_t idesc = p.idesc;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -398,15 +514,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int g = 0; g < num_groups; ++g) {
                     mbar_wait(&a_full[as], aph);
                     uint32_t a_lo = a_base + as * a_stage16;
+                    const uint32_t a_stage_lo = a_lo;
+                    uint32_t a_hi = dhi;
+                    int tap_r = 0, tap_s = 0;
                     for (int j = 0; j < grp; ++j) {
+                        if (wide) {
+                            a_lo = a_stage_lo + (tap_r * p.patch_pw + tap_s) * row16;
+                            a_hi = dhi_wide;  // base-offset field stays 0: the swizzle is a function of the absolute smem address (measured)
+                            if (++tap_s == p.kw) { tap_s = 0; ++tap_r; }
+                        }
+                        const bool stage_first = !p.b_grouped || j == 0, stage_last = !p.b_grouped || j == grp - 1;
                         if (p.b_resident) {
                             bs = g;  // non-patch: group index == k-block index
                             if (tile == tile0) mbar_wait(&b_full[bs], 0);
-                        } else {
+                        } else if (stage_first) {
                             mbar_wait(&b_full[bs], bph);
                         }
                         tc_fence_after();
-                        const uint32_t b_lo = b_base + bs * b_stage16;
+                        const uint32_t b_lo = b_base + bs * b_stage16 + (p.b_grouped ? j * b_sub16 : 0u);
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -414,21 +539,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                                     for (int mi = 0; mi < MT; ++mi) {
                                         if (CG == 2)
-                                            umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
-                                                                 (accum | k) != 0 ? 1u : 0u);
+                                            umma_f16_ss_lohi_ab_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, a_hi, b_lo + 2 * k, dhi, idesc,
+                                                                    (accum | k) != 0 ? 1u : 0u);
                                         else
-                                            umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc,
-                                                             (accum | k) != 0 ? 1u : 0u);
+                                            umma_f16_ss_lohi_ab(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, a_hi, b_lo + 2 * k, dhi, idesc,
+                                                                (accum | k) != 0 ? 1u : 0u);
                                     }
                                 }
                             }
                             if (CG == 2) {  // every release / publication reaches both CTAs of the pair
-                                umma_commit_cg2(&b_empty[bs], 3);
+                                if (stage_last) umma_commit_cg2(&b_empty[bs], 3);
                                 if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
                                 if (j == grp - 1 && g == num_groups - 1) umma_commit_cg2(&tmem_full[acc], 3);
                             } else {
-                                if (p.b_resident) {}
-                                else if (csize == 1) umma_commit(&b_empty[bs]);
+                                if (p.b_resident || !stage_last) {}
+                                else if (p.cluster_n == 1) umma_commit(&b_empty[bs]);
                                 else umma_commit_mcast(&b_empty[bs], cmask);
                                 if (j == grp - 1) umma_commit(&a_empty[as]);
                                 if (j == grp - 1 && g == num_groups - 1) umma_commit(&tmem_full[acc]);
@@ -436,7 +561,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         __syncwarp();
                         accum = 1;
-                        if (!p.b_resident && ++bs == p.b_stages) { bs = 0; bph ^= 1; }
+                        if (!p.b_resident && stage_last && ++bs == p.b_stages) { bs = 0; bph ^= 1; }
                         a_lo += a_shift16;
                     }
                     if (++as == p.a_stages) { as = 0; aph ^= 1; }
@@ -770,6 +895,7 @@ struct PlanCommon {
     ConvParams p;
     int block_n, epi, mt, grid, cluster;
     int cg;  // 2 = CTA-pair MMA (cta_group::2): cluster == 2, each CTA stages half of every weight tile
+    int const_weights;  // desc.reserved bit 6: the weights are not written by the kernel that precedes this one in the stream
     uint32_t smem_bytes;
 };
 
@@ -778,7 +904,9 @@ struct PlanCommon {
 int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1, int cg = 1) {
     ConvParams& p = pc.p;
     pc.cg = cg;
+    p.cluster_n = cluster;
     p.a_stage_bytes = mt * p.a_sub_bytes;
+    if (p.patch_pw > 0) p.a_stage_bytes = static_cast<uint32_t>(p.th + p.kh - 1) * p.patch_pw * p.block_k * 2;  // one shared patch per stage
     p.num_m_super = (p.num_m_tiles + mt - 1) / mt;
     p.num_n_tiles = epi == 1 ? p.na : (p.N + block_n - 1) / block_n;
     p.bias_n = p.num_n_tiles * block_n;
@@ -791,7 +919,11 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1, i
     // tuning knobs (A/B runs): Y5_STAGE_CAP=1 restores the round-1 rule "no more stages than k-blocks + 1";
     // Y5_B_RESIDENT=1 turns the resident-weights mode on (measured 5-15 % slower on the 1x1 layers of yolov5l: opt-in)
     static const bool stage_cap = [] { const char* e = getenv("Y5_STAGE_CAP"); return e && e[0] == '1'; }();
-    static const bool allow_resident = [] { const char* e = getenv("Y5_B_RESIDENT"); return e && e[0] == '1'; }();  // measured slower: opt-in
+    // With constant weights (desc.reserved bit 6) the resident tile is fetched before the PDL dependency wait, i.e. during the
+    // previous kernel's tail, which removes the start-up serialisation that made mode 1 slower -- measured equal to streaming
+    // (profiles/r02_tile_store_sweep.md), so it stays opt-in: Y5_B_RESIDENT=1.
+    static const int resident_env = [] { const char* e = getenv("Y5_B_RESIDENT"); return e ? atoi(e) : 0; }();
+    const bool allow_resident = resident_env == 1;
     p.b_resident = 0;
     if (!patch && allow_resident && cluster == 1 && p.num_n_tiles == 1 && num_kb <= kMaxStages &&
         static_cast<uint32_t>(num_kb) * p.b_stage_bytes <= 132u * 1024u) {
@@ -800,7 +932,7 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1, i
         // weight share (half of it for a 128x128x128 1x1 conv) and deepens the activation prefetch.
         for (int s = kMaxStages; s >= 2; --s)
             if (smem_layout(lay, p.no, p.bias_n, s, num_kb, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = s; break; }
-        if (a_st >= 2) { b_st = num_kb < 2 ? 2 : num_kb; p.b_resident = 1; }
+        if (a_st >= 2) { b_st = num_kb < 2 ? 2 : num_kb; p.b_resident = pc.const_weights ? 2 : 1; }
     }
     if (p.b_resident) {
     } else if (!patch) {
@@ -808,8 +940,9 @@ int finish_plan(PlanCommon& pc, int block_n, int epi, int mt, int cluster = 1, i
             if (smem_layout(lay, p.no, p.bias_n, s, s, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = b_st = s; break; }
         if (stage_cap && a_st > num_kb + 1) a_st = b_st = (num_kb + 1 < 2 ? 2 : num_kb + 1);
     } else {
+        const int b_min = p.b_grouped ? 2 : 3, b_max = p.b_grouped ? 4 : kMaxStages;  // a grouped stage holds kh tiles
         for (int a = 3; a >= 2 && !a_st; --a)
-            for (int b = kMaxStages; b >= 3; --b)
+            for (int b = b_max; b >= b_min; --b)
                 if (smem_layout(lay, p.no, p.bias_n, a, b, p.a_stage_bytes, p.b_stage_bytes).total <= budget) { a_st = a; b_st = b; break; }
     }
     if (a_st < 2 || b_st < 2) return set_error(Y5_E_UNSUPPORTED, "conv tile does not fit shared memory (block_n %d a %u b %u)", block_n,
@@ -831,6 +964,7 @@ int run_plan(const PlanCommon& pc, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
     const int key = (pc.cg == 2 ? 100000 : 0) + pc.epi * 10000 + pc.block_n * 10 + pc.mt;
     switch (key) {
+        case 100642: e = launch_conv<64, 0, 2, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 101281: e = launch_conv<128, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 101282: e = launch_conv<128, 0, 2, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
         case 102561: e = launch_conv<256, 0, 1, 2>(pc.tmA, pc.tmB, pc.tmC, pc.p, pc.grid, 2, pc.smem_bytes, st); break;
@@ -939,7 +1073,7 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
         else {  // forced block_n (tests / tuning): reserved bit 1 asks for MT = 2, bits 8.. give the cluster size
             mt_sel = bn < 128 ? 128 / bn : ((d->reserved & 2) ? 2 : 1);
             cl_sel = (d->reserved >> 8) > 1 ? (d->reserved >> 8) : 1;
-            if ((d->reserved & 4) && bn >= 128) { cg_sel = 2; cl_sel = 2; }  // CTA-pair MMA
+            if ((d->reserved & 4) && bn >= 64) { cg_sel = 2; cl_sel = 2; }  // CTA-pair MMA (64-wide tiles: two sub-tiles per CTA)
         }
         if (const char* e = getenv("Y5_CLUSTER")) cl_sel = atoi(e) > 1 && bn >= 128 ? atoi(e) : 1;
         if (const char* e = getenv("Y5_BIG_TILE")) {  // tuning: "<block_n>x<mt>" for layers with out_c >= 256, e.g. 256x1
@@ -990,11 +1124,20 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
                 if (pair_tiles >= 60) { bn = 128; mt_sel = mt2; cg_sel = 2; cl_sel = 2; }
             }
         }
+        // 64 output channels, k > 1: these layers are bound by the MMA ISSUE rate (one elected thread issues ~1 tcgen05.mma per
+        // ~130 clocks whatever its size; a 128x64x16 MMA is 32 clocks of tensor work) -> pairs double the work per issued
+        // instruction (256x64x16).  Y5_CG2_N64=0 disables.
+        static const bool cg2_n64 = [] { const char* e = getenv("Y5_CG2_N64"); return !(e && e[0] == '0'); }();
+        if (!d->block_n && cg2_mode > 0 && cg2_n64 && cg_sel == 1 && d->out_c == 64 && a_mode_sel != A_LINEAR) {
+            const long long m_tiles = (M64 + kBlockM - 1) / kBlockM;
+            if ((m_tiles + 3) / 4 >= 60) { bn = 64; mt_sel = 2; cg_sel = 2; cl_sel = 2; }
+        }
     }
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
     auto* plan = new y5_conv_plan();
     PlanCommon& pc = plan->pc;
     std::memset(&pc.p, 0, sizeof(pc.p));
+    pc.const_weights = (d->reserved & 64) ? 1 : 0;
     ConvParams& p = pc.p;
     p.M = static_cast<int>(M64);
     p.N = d->out_c;
@@ -1014,7 +1157,8 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     p.block_k = bk;
     p.c_chunks = (d->in_c + bk - 1) / bk;
     const int row_bytes = bk * 2;
-    p.b_stage_bytes = bn / cg_sel * row_bytes;  // pair mode: each CTA stages half of the weight tile's rows
+    p.b_sub_bytes = bn / cg_sel * row_bytes;  // pair mode: each CTA stages half of the weight tile's rows
+    p.b_stage_bytes = p.b_sub_bytes;
     p.a_mode = a_mode_sel;
 
     const CUtensorMapSwizzle sw = swizzle_for_row_bytes(row_bytes);
@@ -1034,15 +1178,39 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
     } else {
         p.tw = best_tw;
         p.th = 128 / best_tw;
+        // wide patch mode (see the header): 128-byte rows, horizontal taps, and an 8-pixel-wide tiling that wastes no more than the
+        // chosen one; with MT = 2 the two sub-tiles must be neighbours in x (even number of 8-pixel tiles per row).
+        // Y5_PATCH_WIDE=1 / reserved bit 7 (128) enable it; reserved bit 5 (32) wins and disables it.
+        static const bool wide_env = [] { const char* e = getenv("Y5_PATCH_WIDE"); return e && e[0] == '1'; }();
+        const bool wide_ok = wide_env || (d->reserved & 128);  // measured 0..-9 % (slower) on yolov5l: opt-in (tests force it with bit 7)
+        {
+            const int tx8 = (g.Wo + 7) / 8, ty16 = (g.Ho + 15) / 16;
+            const double eff8 = (double)g.Wo * g.Ho / ((double)tx8 * 8 * ty16 * 16);
+            if (wide_ok && !(d->reserved & 32) && row_bytes == 128 && g.kw > 1 && g.kw <= 7 && (mt_sel == 1 || (mt_sel == 2 && tx8 % 2 == 0)) &&
+                eff8 >= best_eff - 1e-9) {
+                p.tw = 8;
+                p.th = 16;
+                p.patch_pw = 8 * mt_sel + 8;
+            }
+        }
+        // grouped weight stages: the kh tiles of a (chunk, horizontal tap) group travel in ONE stage -- one full/empty barrier round
+        // and one commit per group instead of per tile.  The MMA-issuing warp is the bottleneck of the narrow layers (ncu: it never
+        // waits on a barrier, ~120 instructions per 8 MMAs at ~9 clocks each), so fewer round trips per MMA is what pays.
+        // Y5_B_GROUP: 0 off, 1 (default) tiles up to 128 channels wide, 2 every patch-mode layer.
+        static const int group_mode = [] { const char* e = getenv("Y5_B_GROUP"); return e ? atoi(e) : 1; }();
+        if (!p.patch_pw && g.kh > 1 && cl_sel == cg_sel && (group_mode == 2 || (group_mode == 1 && bn <= 128))) {
+            p.b_grouped = 1;
+            p.b_stage_bytes = g.kh * p.b_sub_bytes;
+        }
         p.tiles_x = (g.Wo + p.tw - 1) / p.tw;
         p.tiles_y = (g.Ho + p.th - 1) / p.th;
         p.rcp_tiles_x = 1.0f / static_cast<float>(p.tiles_x);
         p.rcp_per_img = 1.0f / static_cast<float>(p.tiles_x * p.tiles_y);
         p.num_m_tiles = d->batch * p.tiles_x * p.tiles_y;
-        p.a_sub_bytes = (p.th + g.kh - 1) * p.tw * row_bytes;
+        p.a_sub_bytes = p.patch_pw ? 8 * row_bytes : (p.th + g.kh - 1) * p.tw * row_bytes;
         cuuint64_t dims[4] = {(cuuint64_t)d->in_c, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->batch};
         cuuint64_t str[3] = {(cuuint64_t)g.xs * 2, (cuuint64_t)g.ys * 2, (cuuint64_t)g.ns * 2};
-        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)(p.th + g.kh - 1), 1};
+        cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(p.patch_pw ? p.patch_pw : p.tw), (cuuint32_t)(p.th + g.kh - 1), 1};
         e = encode_tiled(&pc.tmA, d->dtype, d->in, 4, dims, str, box, sw, "A patch");
     }
     if (e) { delete plan; return e; }

@@ -228,6 +228,7 @@ class Program:
         d.a_mode = int(os.environ.get("Y5_FORCE_A_MODE", "0"))
         if d.a_mode == 2 and s != 1:
             d.a_mode = 0
+        d.reserved = 64  # packed once at build time: constant weights, the kernel may fetch them before its dependency wait
         plan = C.c_void_p()
         _lib.check(self.lib.y5_conv_plan_create(C.byref(d), C.byref(plan)), f"conv_plan_create[{name}]")
         self._plans.append((self.lib.y5_conv_plan_destroy, plan))
