@@ -230,14 +230,12 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         uint32_t accum = 0;
         for (int g = 0; g < num_groups; ++g) {
-            mbar_wait(&a_full[as], aph);
+            mbar_wait(&a_full[as], aph);  // !PATCH: the stage's activation AND weight tiles (one barrier pair per stage, see producer_lean)
             uint32_t a_lo = a_base + as * a_stage16;
             const bool last_group = g == num_groups - 1;
-            for (int j = 0; j < grp; ++j) {
-                const bool stage_first = !GROUPED || j == 0, stage_last = !GROUPED || j == grp - 1;
-                if (stage_first) mbar_wait(&b_full[bs], bph);
+            if (!PATCH) {
                 tc_fence_after();
-                const uint32_t b_lo = b_base + bs * b_stage16 + (GROUPED ? j * b_sub16 : 0u);
+                const uint32_t b_lo = b_base + as * b_stage16;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -248,23 +246,170 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
                         }
                     }
                     if (CG == 2) {
-                        if (stage_last) umma_commit_cg2(&b_empty[bs], 3);
-                        if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
-                        if (j == grp - 1 && last_group) umma_commit_cg2(&tmem_full[acc], 3);
+                        umma_commit_cg2(&a_empty[as], 3);
+                        if (last_group) umma_commit_cg2(&tmem_full[acc], 3);
                     } else {
-                        if (stage_last) umma_commit(&b_empty[bs]);
-                        if (j == grp - 1) umma_commit(&a_empty[as]);
-                        if (j == grp - 1 && last_group) umma_commit(&tmem_full[acc]);
+                        umma_commit(&a_empty[as]);
+                        if (last_group) umma_commit(&tmem_full[acc]);
                     }
                 }
                 __syncwarp();
                 accum = 1;
-                if (stage_last && ++bs == b_stages) { bs = 0; bph ^= 1; }
-                a_lo += a_shift16;
+            } else {
+                for (int j = 0; j < grp; ++j) {
+                    const bool stage_first = !GROUPED || j == 0, stage_last = !GROUPED || j == grp - 1;
+                    if (stage_first) mbar_wait(&b_full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t b_lo = b_base + bs * b_stage16 + (GROUPED ? j * b_sub16 : 0u);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                            for (int mi = 0; mi < MT; ++mi) {
+                                if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                                else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                            }
+                        }
+                        if (CG == 2) {
+                            if (stage_last) umma_commit_cg2(&b_empty[bs], 3);
+                            if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
+                            if (j == grp - 1 && last_group) umma_commit_cg2(&tmem_full[acc], 3);
+                        } else {
+                            if (stage_last) umma_commit(&b_empty[bs]);
+                            if (j == grp - 1) umma_commit(&a_empty[as]);
+                            if (j == grp - 1 && last_group) umma_commit(&tmem_full[acc]);
+                        }
+                    }
+                    __syncwarp();
+                    accum = 1;
+                    if (stage_last && ++bs == b_stages) { bs = 0; bph ^= 1; }
+                    a_lo += a_shift16;
+                }
             }
             if (++as == a_stages) { as = 0; aph ^= 1; }
         }
         if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+    }
+}
+
+// The TMA-issuing warp's loop, specialised the same way (it is the other single-warp instruction stream of the kernel: for 1x1
+// and TMA-im2col layers, one activation + one weight copy per K block, it is the longer of the two).
+//   MODE != A_PATCH : activation and weight tile of a K block share ONE full / empty barrier pair (same ring index): half the
+//                     barrier round trips for this warp and for the MMA warp
+//   MODE == A_PATCH : per (chunk, horizontal tap) group one activation patch per sub-tile and kh weight tiles (GROUPED: in one stage)
+template <int BLOCK_N, int MT, int CG, int MODE, bool GROUPED>
+__device__ __forceinline__ void producer_lean(const CUtensorMap* tmA, const CUtensorMap* tmB, const ConvParams& p, uint8_t* sA, uint8_t* sB,
+                                              uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty, uint32_t crank, int tile0,
+                                              int tile_step, int num_tiles) {
+    const int csz = CG;  // lean mode: the cluster is exactly the CTA pair (or a single CTA)
+    const int nn = p.num_n_tiles;
+    const int step_q = tile_step / nn, step_r = tile_step - step_q * nn;
+    int tq = tile0 / nn, tr = tile0 - tq * nn;
+    const uint32_t a_stage_bytes = p.a_stage_bytes, b_stage_bytes = p.b_stage_bytes, a_sub_bytes = p.a_sub_bytes, b_sub_bytes = p.b_sub_bytes;
+    const int a_stages = p.a_stages, b_stages = p.b_stages;
+    const int c_chunks = p.c_chunks, kw = p.kw, kh = p.kh;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int ms = tq * csz + static_cast<int>(crank);
+        const int n0 = tr * BLOCK_N + (CG == 2 ? static_cast<int>(crank) * (BLOCK_N / 2) : 0);  // pair mode: my half of the weight rows
+        tq += step_q;
+        tr += step_r;
+        if (tr >= nn) { tr -= nn; ++tq; }
+        int img[MT], y0[MT], x0[MT];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const int mt = ms * MT + mi;
+            img[mi] = y0[mi] = x0[mi] = 0;
+            if (MODE == A_IM2COL) {
+                const int m0 = mt * kBlockM;
+                img[mi] = fdiv(m0, p.HoWo, p.rcp_HoWo);
+                const int rem = m0 - img[mi] * p.HoWo;
+                const int oy = fdiv(rem, p.Wo, p.rcp_Wo);
+                y0[mi] = oy * p.stride - p.pad_h;
+                x0[mi] = (rem - oy * p.Wo) * p.stride - p.pad_w;
+            } else if (MODE == A_PATCH) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                img[mi] = fdiv(mt, per_img, p.rcp_per_img);
+                const int rem = mt - img[mi] * per_img;
+                const int ty = fdiv(rem, p.tiles_x, p.rcp_tiles_x);
+                y0[mi] = ty * p.th - p.pad_h;
+                x0[mi] = (rem - ty * p.tiles_x) * p.tw - p.pad_w;
+            }
+        }
+        if (MODE != A_PATCH) {
+            int r = 0, sx = 0, cc = 0;
+            const int num_kb = kh * kw * c_chunks;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&a_empty[as], aph ^ 1);
+                if (elect_one()) {
+                    if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&a_full[as], CG * (a_stage_bytes + b_stage_bytes));
+                    const uint32_t bar = CG == 2 ? mapa_u32(&a_full[as], 0) : 0;
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi) {
+                        uint8_t* a_dst = sA + as * a_stage_bytes + mi * a_sub_bytes;
+                        if (MODE == A_LINEAR) {
+                            if (CG == 2) tma_load_2d_cg2(tmA, bar, a_dst, cc * 64, (ms * MT + mi) * kBlockM);
+                            else tma_load_2d(tmA, &a_full[as], a_dst, cc * 64, (ms * MT + mi) * kBlockM);
+                        } else {
+                            if (CG == 2)
+                                tma_load_im2col_4d_cg2(tmA, bar, a_dst, cc * 64, x0[mi], y0[mi], img[mi], static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                            else
+                                tma_load_im2col_4d(tmA, &a_full[as], a_dst, cc * 64, x0[mi], y0[mi], img[mi], static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                        }
+                    }
+                    if (CG == 2) tma_load_2d_cg2(tmB, bar, sB + as * b_stage_bytes, kb * 64, n0);
+                    else tma_load_2d(tmB, &a_full[as], sB + as * b_stage_bytes, kb * 64, n0);
+                }
+                __syncwarp();
+                if (++as == a_stages) { as = 0; aph ^= 1; }
+                if (++cc == c_chunks) { cc = 0; if (++sx == kw) { sx = 0; ++r; } }
+            }
+        } else {
+            for (int cc = 0; cc < c_chunks; ++cc) {
+                for (int sx = 0; sx < kw; ++sx) {
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    if (GROUPED) mbar_wait(&b_empty[bs], bph ^ 1);
+                    if (elect_one()) {
+                        if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&a_full[as], CG * a_stage_bytes);
+                        const uint32_t a_bar = CG == 2 ? mapa_u32(&a_full[as], 0) : 0;
+#pragma unroll
+                        for (int mi = 0; mi < MT; ++mi) {
+                            uint8_t* a_dst = sA + as * a_stage_bytes + mi * a_sub_bytes;
+                            if (CG == 2) tma_load_4d_cg2(tmA, a_bar, a_dst, cc * 64, x0[mi] + sx, y0[mi], img[mi]);
+                            else tma_load_4d(tmA, &a_full[as], a_dst, cc * 64, x0[mi] + sx, y0[mi], img[mi]);
+                        }
+                        if (GROUPED) {
+                            if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&b_full[bs], CG * b_stage_bytes);
+                            const uint32_t b_bar = CG == 2 ? mapa_u32(&b_full[bs], 0) : 0;
+                            for (int j = 0; j < kh; ++j) {
+                                const int kb = (j * kw + sx) * c_chunks + cc;
+                                uint8_t* b_dst = sB + bs * b_stage_bytes + j * b_sub_bytes;
+                                if (CG == 2) tma_load_2d_cg2(tmB, b_bar, b_dst, kb * 64, n0);
+                                else tma_load_2d(tmB, &b_full[bs], b_dst, kb * 64, n0);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (++as == a_stages) { as = 0; aph ^= 1; }
+                    if (GROUPED) {
+                        if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                    } else {
+                        for (int j = 0; j < kh; ++j) {
+                            const int kb = (j * kw + sx) * c_chunks + cc;
+                            mbar_wait(&b_empty[bs], bph ^ 1);
+                            if (elect_one()) {
+                                if (CG == 1 || crank == 0) mbar_arrive_expect_tx(&b_full[bs], CG * b_stage_bytes);
+                                if (CG == 2) tma_load_2d_cg2(tmB, mapa_u32(&b_full[bs], 0), sB + bs * b_stage_bytes, kb * 64, n0);
+                                else tma_load_2d(tmB, &b_full[bs], sB + bs * b_stage_bytes, kb * 64, n0);
+                            }
+                            __syncwarp();
+                            if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -374,7 +519,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int grp = wide ? p.kh * p.kw : (patch ? p.kh : 1);
     const int num_groups = wide ? p.c_chunks : (patch ? p.c_chunks * p.kw : p.kh * p.kw * p.c_chunks);
 
-    if (warp == 0) {
+    // the common case -- 64-channel chunks, streamed weights, no weight multicast, no wide patch -- runs specialised loops in both
+    // single-warp roles (see mma_issue_lean / producer_lean); everything else takes the generic loops below
+    const bool lean = p.block_k == 64 && !p.b_resident && !wide && p.cluster_n == CG;
+    if (warp == 0 && lean) {
+        if (p.a_mode == A_LINEAR)
+            producer_lean<BLOCK_N, MT, CG, A_LINEAR, false>(&tmA, &tmB, p, sA, sB, a_full, a_empty, b_full, b_empty, crank, tile0, tile_step, num_tiles);
+        else if (p.a_mode == A_IM2COL)
+            producer_lean<BLOCK_N, MT, CG, A_IM2COL, false>(&tmA, &tmB, p, sA, sB, a_full, a_empty, b_full, b_empty, crank, tile0, tile_step, num_tiles);
+        else if (p.b_grouped)
+            producer_lean<BLOCK_N, MT, CG, A_PATCH, true>(&tmA, &tmB, p, sA, sB, a_full, a_empty, b_full, b_empty, crank, tile0, tile_step, num_tiles);
+        else
+            producer_lean<BLOCK_N, MT, CG, A_PATCH, false>(&tmA, &tmB, p, sA, sB, a_full, a_empty, b_full, b_empty, crank, tile0, tile_step, num_tiles);
+    } else if (warp == 0) {
         // ===================================== TMA producer =====================================
         {   // the whole warp runs the loop with warp-uniform state; one elected lane issues the copies (keeps the TMA
             // operands in uniform registers: a divergent `lane == 0` region makes the compiler wrap every UTMALDG in a
@@ -480,7 +637,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        const bool lean = EPI == 0 && p.block_k == 64 && !p.b_resident && !wide && p.cluster_n == CG;
         if ((CG == 1 || crank == 0) && lean) {   // the common case: specialised straight-line loops (see mma_issue_lean)
             const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
             if (!patch)
