@@ -255,12 +255,42 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
                 }
                 __syncwarp();
                 accum = 1;
+            } else if (GROUPED) {  // the group's kh weight tiles arrived together: one wait, one elected region, one commit each
+                mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                uint32_t b_lo = b_base + bs * b_stage16;
+                if (elect_one()) {
+                    for (int j = 0; j < grp; ++j) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                            for (int mi = 0; mi < MT; ++mi) {
+                                if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                                else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
+                            }
+                        }
+                        accum = 1;
+                        a_lo += a_shift16;
+                        b_lo += b_sub16;
+                    }
+                    if (CG == 2) {
+                        umma_commit_cg2(&b_empty[bs], 3);
+                        umma_commit_cg2(&a_empty[as], 3);
+                        if (last_group) umma_commit_cg2(&tmem_full[acc], 3);
+                    } else {
+                        umma_commit(&b_empty[bs]);
+                        umma_commit(&a_empty[as]);
+                        if (last_group) umma_commit(&tmem_full[acc]);
+                    }
+                }
+                __syncwarp();
+                accum = 1;
+                if (++bs == b_stages) { bs = 0; bph ^= 1; }
             } else {
                 for (int j = 0; j < grp; ++j) {
-                    const bool stage_first = !GROUPED || j == 0, stage_last = !GROUPED || j == grp - 1;
-                    if (stage_first) mbar_wait(&b_full[bs], bph);
+                    mbar_wait(&b_full[bs], bph);
                     tc_fence_after();
-                    const uint32_t b_lo = b_base + bs * b_stage16 + (GROUPED ? j * b_sub16 : 0u);
+                    const uint32_t b_lo = b_base + bs * b_stage16;
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -271,18 +301,18 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
                             }
                         }
                         if (CG == 2) {
-                            if (stage_last) umma_commit_cg2(&b_empty[bs], 3);
+                            umma_commit_cg2(&b_empty[bs], 3);
                             if (j == grp - 1) umma_commit_cg2(&a_empty[as], 3);
                             if (j == grp - 1 && last_group) umma_commit_cg2(&tmem_full[acc], 3);
                         } else {
-                            if (stage_last) umma_commit(&b_empty[bs]);
+                            umma_commit(&b_empty[bs]);
                             if (j == grp - 1) umma_commit(&a_empty[as]);
                             if (j == grp - 1 && last_group) umma_commit(&tmem_full[acc]);
                         }
                     }
                     __syncwarp();
                     accum = 1;
-                    if (stage_last && ++bs == b_stages) { bs = 0; bph ^= 1; }
+                    if (++bs == b_stages) { bs = 0; bph ^= 1; }
                     a_lo += a_shift16;
                 }
             }
@@ -1266,10 +1296,10 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
                 const long long pair_tiles = ((m_tiles + 1) / 2) * (d->out_c / bn2);
                 if (pair_tiles >= 60) { bn = bn2; mt_sel = 1; cg_sel = 2; cl_sel = 2; }
                 // 512 x 256 pair tiles (two sub-tiles per CTA, all 512 TMEM columns, single-buffered accumulators): half the weight
-                // bytes per flop again.  Measured (profiles/r02_tile_store_sweep.md): -6..-19 % on the stride-2 TMA-im2col layers when
-                // there are >= ~150 such tiles (model.3/5/7/18 of yolov5l), +17..+32 % on shifted-patch layers (their activation
-                // patches leave room for two stages only) -> im2col stride >= 2 only.  Y5_CG2_MT2=0 off, 1 = every non-1x1 layer.
-                static const int mt2_pairs = [] { const char* e = getenv("Y5_CG2_MT2"); return e ? atoi(e) : 2; }();
+                // bytes per flop again.  They paid (-6..-19 % on the stride-2 layers) while the generic single-warp loops bounded the
+                // kernel; with the specialised loops the double-buffered 256 x 256 tiles win everywhere (model.3 199 -> 160 us,
+                // model.5 179 -> 148 us): off by default.  Y5_CG2_MT2=2 restores the stride-2 rule, 1 = every non-1x1 layer.
+                static const int mt2_pairs = [] { const char* e = getenv("Y5_CG2_MT2"); return e ? atoi(e) : 0; }();
                 const long long tiles_mt2 = ((m_tiles + 3) / 4) * (d->out_c / 256);
                 if (mt2_pairs && cg_sel == 2 && bn == 256 && !linear &&
                     (mt2_pairs == 1 ? tiles_mt2 >= 60 : (a_mode_sel == A_IM2COL && d->stride >= 2 && tiles_mt2 >= 150)))
@@ -1289,6 +1319,12 @@ extern "C" Y5_API int y5_conv_plan_create(const y5_conv_desc* d, y5_conv_plan** 
             if ((m_tiles + 3) / 4 >= 60) { bn = 64; mt_sel = 2; cg_sel = 2; cl_sel = 2; }
         }
     }
+    // 256-wide tiles: the TMA-im2col path shares one barrier pair between the activation and the weight tile of a K block, the
+    // patch path keeps two rings; with the single-warp instruction streams as the bound that is worth more than the patch mode's
+    // smaller L2 traffic (measured: 99 -> 87 us on yolov5l's 256-channel 3x3 layers).  Narrower tiles keep the patch mode: their kh
+    // weight tiles travel in one grouped stage.  Y5_PATCH_256=1 restores the patch mode for them.
+    static const bool patch_256 = [] { const char* e = getenv("Y5_PATCH_256"); return e && e[0] == '1'; }();
+    if (a_mode_sel == A_PATCH && d->a_mode == 0 && bn == 256 && !patch_256) a_mode_sel = A_IM2COL;
     if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(Y5_E_INVALID, "conv: block_n must be 32/64/128/256");
     auto* plan = new y5_conv_plan();
     PlanCommon& pc = plan->pc;
