@@ -49,7 +49,8 @@ namespace y5 {
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;  // warp0 producer, warp1 mma, warps 2..17 epilogue
+constexpr int kThreads = 64 + kEpiThreads + 32;  // warp0 producer, warp1 mma, warps 2..17 epilogue, warp 18 second mma issuer (MT == 2)
+constexpr int kMma2Warp = 2 + kEpiWarps;         // (96 registers per thread either way: the allocation granule covers 640 threads)
 constexpr int kMaxStages = 8;
 constexpr int kHeadN = 128;                 // head GEMM: one anchor per 128-wide N tile (no <= 128)
 
@@ -209,7 +210,10 @@ __device__ __forceinline__ void head_chunk(const uint32_t (&v)[32], const float*
 // kernel; the generic loop in the kernel body handles the rest.
 //   PATCH   : A groups of kh weight tiles (vertical taps read the same activation patch at row offsets)
 //   GROUPED : the kh tiles of a group share one weight stage (one barrier round and one commit per group)
-template <int BLOCK_N, int MT, int CG, bool PATCH, bool GROUPED>
+//   MI0, MI1: the sub-tiles [MI0, MI1) this warp issues for.  With MT == 2 two warps run this loop, one per sub-tile (independent
+//             accumulators, same operand stages): the MMA stream, the longest of the kernel for narrow tiles, is halved; every
+//             "empty" / "accumulator full" barrier then expects one commit from each of them.
+template <int BLOCK_N, int MT, int CG, bool PATCH, bool GROUPED, int MI0 = 0, int MI1 = MT>
 __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
                                                int tile0, int tile_step, int num_tiles) {
@@ -240,7 +244,7 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                        for (int mi = 0; mi < MT; ++mi) {
+                        for (int mi = MI0; mi < MI1; ++mi) {
                             if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                             else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                         }
@@ -264,7 +268,7 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                            for (int mi = 0; mi < MT; ++mi) {
+                            for (int mi = MI0; mi < MI1; ++mi) {
                                 if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                                 else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                             }
@@ -295,7 +299,7 @@ __device__ __forceinline__ void mma_issue_lean(const ConvParams& p, uint64_t* a_
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                            for (int mi = 0; mi < MT; ++mi) {
+                            for (int mi = MI0; mi < MI1; ++mi) {
                                 if (CG == 2) umma_f16_ss_lohi_cg2(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                                 else umma_f16_ss_lohi(d_tmem + mi * BLOCK_N, a_lo + mi * a_sub16 + 2 * k, b_lo + 2 * k, dhi, idesc, accum | k);
                             }
@@ -483,24 +487,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t crank = cluster_ctarank();
     const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
 
+    // MT == 2 on the specialised loops: two MMA-issuing warps, one per sub-tile (see mma_issue_lean)
+    const bool dual_mma = MT == 2 && p.block_k == 64 && !p.b_resident && p.patch_pw == 0 && p.cluster_n == CG;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (EPI == 0 && p.tma_store) tma_prefetch_desc(&tmC);
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
+            mbar_init(&a_empty[s], dual_mma ? 2 : 1);
             mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], CG == 2 ? 1 : csize);  // multicast mode: released by the MMA thread of every CTA in the cluster
+            mbar_init(&b_empty[s], dual_mma ? 2 : (CG == 2 ? 1 : csize));  // multicast mode: released by the MMA thread of every CTA in the cluster
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_full[s], dual_mma ? 2 : 1);
             mbar_init(&tmem_empty[s], CG * kEpiWarps);  // pair mode: the epilogue warps of both CTAs release the leader's barrier
         }
         fence_barrier_init();
     }
     if (warp == 1) { if (CG == 2) tmem_alloc_cg2(tmem_ptr_smem, kTmemCols); else tmem_alloc(tmem_ptr_smem, kTmemCols); }
-    if (warp >= 2)  // whole folded-BN bias vector once: no per-tile global loads on the epilogue's critical path
+    if (warp >= 2 && warp < kMma2Warp)  // whole folded-BN bias vector once: no per-tile global loads on the epilogue's critical path
         for (int i = threadIdx.x - 64; i < p.bias_n; i += kEpiThreads) {
             // SiLU layers keep HALF the bias: the epilogue forms h = (acc + b) / 2 with one FMA and silu = h + h * tanh(h)
             const float b = i < p.N ? __ldg(p.bias + i) : 0.0f;
@@ -669,15 +675,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================================== MMA issuer =====================================
         if ((CG == 1 || crank == 0) && lean) {   // the common case: specialised straight-line loops (see mma_issue_lean)
             const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
+            constexpr int M1 = MT == 2 ? 1 : MT;  // MT == 2: this warp issues sub-tile 0, warp kMma2Warp sub-tile 1
             if (!patch)
-                mma_issue_lean<BLOCK_N, MT, CG, false, false>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
-                                                              tile_step, num_tiles);
+                mma_issue_lean<BLOCK_N, MT, CG, false, false, 0, M1>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                     tile0, tile_step, num_tiles);
             else if (p.b_grouped)
-                mma_issue_lean<BLOCK_N, MT, CG, true, true>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
-                                                            tile_step, num_tiles);
+                mma_issue_lean<BLOCK_N, MT, CG, true, true, 0, M1>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                   tile0, tile_step, num_tiles);
             else
-                mma_issue_lean<BLOCK_N, MT, CG, true, false>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base, tile0,
-                                                             tile_step, num_tiles);
+                mma_issue_lean<BLOCK_N, MT, CG, true, false, 0, M1>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                    tile0, tile_step, num_tiles);
         } else if (CG == 1 || crank == 0) {   // pair mode: the leader CTA issues for both.  whole warp, warp-uniform state; the elected lane issues tcgen05.mma / tcgen05.commit (see the producer's note)
             int as = 0, bs = 0, acc = 0;
             uint32_t aph = 0, bph = 0, acc_phase = 0;
@@ -754,6 +761,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
+        }
+    } else if (warp == kMma2Warp) {
+        // ===================================== second MMA issuer (sub-tile 1 of MT == 2 tiles) =====================================
+        if (MT == 2 && dual_mma && (CG == 1 || crank == 0)) {
+            const uint32_t a_base = umma_desc_lo(smem_u32(sA)), b_base = umma_desc_lo(smem_u32(sB));
+            constexpr int M0 = MT == 2 ? 1 : 0;
+            if (!patch)
+                mma_issue_lean<BLOCK_N, MT, CG, false, false, M0, MT>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                      tile0, tile_step, num_tiles);
+            else if (p.b_grouped)
+                mma_issue_lean<BLOCK_N, MT, CG, true, true, M0, MT>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                    tile0, tile_step, num_tiles);
+            else
+                mma_issue_lean<BLOCK_N, MT, CG, true, false, M0, MT>(p, a_full, a_empty, b_full, b_empty, tmem_full, tmem_empty, tmem_base, a_base, b_base,
+                                                                     tile0, tile_step, num_tiles);
         }
     } else {
         // ===================================== epilogue (warps 2..17) =====================================
@@ -945,7 +967,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
 
-    if (EPI == 0 && p.tma_store && warp >= 2 && lane == 0) tma_store_wait_all();  // bulk stores issued by this thread are complete
+    if (EPI == 0 && p.tma_store && warp >= 2 && warp < kMma2Warp && lane == 0) tma_store_wait_all();  // bulk stores issued by this thread are complete
     tc_fence_before();
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer may still arrive on its barriers
