@@ -1021,6 +1021,15 @@ using namespace y5;
 namespace {
 
 int pick_block_k(int in_c) {
+    // 64-channel chunks (128-byte rows) run the specialised single-warp loops (mma_issue_lean / producer_lean); the generic loops
+    // that narrower chunks need cost more than the zero padding of K does (the copy engine zero-fills the channels beyond in_c,
+    // the packed weights carry zeros there).  Only very narrow inputs keep 16-/32-channel chunks.  Y5_BK_RULE=0: the round-1 rule
+    // (fewest padded K elements + a per-chunk cost).
+    // Measured: yolov5m forward 3.49 -> 3.19 ms (its 96-channel layers were on 32-channel chunks), training step 19.5 -> 18.3 ms;
+    // yolov5s forward 1.53 -> 1.46 ms with 64-channel chunks for its 32-channel layers too.
+    static const int rule = [] { const char* e = getenv("Y5_BK_RULE"); return e ? atoi(e) : 2; }();  // 0 round-1 cost rule, 1 = 64 above 32 channels, 2 (default) = 64 above 16
+    if (rule == 1) return in_c > 32 ? 64 : (in_c > 16 ? 32 : 16);
+    if (rule == 2) return in_c > 16 ? 64 : 16;
     int best = 64;
     long best_cost = -1;
     for (int bk : {64, 32, 16}) {
