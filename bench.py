@@ -628,23 +628,29 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
 
     rec = None
     graphed = tc_ref = None
-    if rank == 0 and world == 1 and extras:
-        try:  # whole step replayed from one CUDA graph through the public helper: what the kernels cost without Python
+    graph_dp = world > 1 and os.environ.get("Y5_BENCH_GRAPH_DP", "1") != "0"
+    if (world == 1 and rank == 0 and extras) or graph_dp:
+        # whole step replayed from one CUDA graph through the public helper: what the kernels cost without Python.  N > 1: every
+        # rank captures its step including the ONE all-reduce of the gradient arena (FusedSGD.data_parallel) and replays in lock-step.
+        try:
             gm = build()
             gopt = smart_optimizer(gm, "SGD", lr=1e-3, momentum=hyp["momentum"], decay=hyp["weight_decay"])
-            gstep = GraphedTrainStep(gm, ComputeLoss(gm), gopt, batch=bs, size=size, amp_dtype=tdt, max_norm=10.0, ema=ModelEMA(gm))
+            if world > 1:
+                gopt.data_parallel(gm)
+            gstep = GraphedTrainStep(gm, ComputeLoss(gm), gopt, batch=bs, size=size, amp_dtype=tdt, max_norm=10.0,
+                                     ema=ModelEMA(gm) if rank == 0 else None)
+
+            def g_run(i):
+                host_items.copy_(gstep(host_img[i % n_rot], host_tgt[i % n_rot]), non_blocking=True)
+
             for i in range(2):
-                host_items.copy_(gstep(host_img[i % n_rot], host_tgt[i % n_rot]), non_blocking=True)
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(steps):
-                host_items.copy_(gstep(host_img[i % n_rot], host_tgt[i % n_rot]), non_blocking=True)
-            e1.record()
-            torch.cuda.synchronize(dev)
-            graphed = {"value": bs * steps / (e0.elapsed_time(e1) / 1e3), "unit": "images/s", "ms_per_step": e0.elapsed_time(e1) / steps,
-                       "what": "yolov5_b200.utils.torch_utils.GraphedTrainStep: the same step (dynamic loss scale, clip, fused SGD, EMA) captured "
-                               "once in a CUDA graph, replayed per batch with pinned-host uint8 images + labels uploaded and loss items downloaded"}
+                g_run(i)
+            g_ms = timed(D, g_run, steps)
+            g_images, g_worst = aggregate_throughput(bs * steps, g_ms, dev)
+            graphed = {"value": g_images / (g_worst / 1e3), "unit": "images/s", "ms_per_step": g_worst / steps,
+                       "what": "yolov5_b200.utils.torch_utils.GraphedTrainStep: the same step (dynamic loss scale, clip, fused SGD, EMA"
+                               + (", the gradient all-reduce" if world > 1 else "") + ") captured once in a CUDA graph per rank, replayed per batch "
+                               "with pinned-host uint8 images + labels uploaded and loss items downloaded"}
             del gstep, gm, gopt
         except Exception as ex:  # noqa: BLE001
             graphed = {"unavailable": repr(ex)[:300]}

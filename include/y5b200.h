@@ -274,6 +274,21 @@ int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int32_t channels, int
  * (padding channels zero; pads = channel counts rounded up to the block_k y5_conv_pick returns). */
 int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t ksize, void* fwd, int32_t in_c_pad,
                    void* dgrad, int32_t out_c_pad, int32_t dtype, void* stream);
+/* The same for every filter of a model in ONE launch (the training step re-packs its fp32 master weights once per forward):
+ * `items` (device memory) describes the filters exactly like the arguments of y5_weight_pack; block b of the launch converts
+ * elements [chunk_index[b] * y5_weight_pack_chunk_elems(), ...) of the concatenated [fwd | dgrad] packing of item chunk_item[b]
+ * (both arrays in device memory, built once per model by the caller). */
+typedef struct y5_pack_item {
+    const void* w;
+    void* fwd;
+    void* dgrad;
+    int32_t w_dtype;
+    int32_t out_c, in_c, ksize;
+    int32_t in_c_pad, out_c_pad;
+} y5_pack_item;
+int32_t y5_weight_pack_chunk_elems(void);
+int y5_weight_pack_multi(const y5_pack_item* items, const int32_t* chunk_item, const int32_t* chunk_index, int32_t n_chunks,
+                         int32_t dtype, void* stream);
 /* backward of y5_upsample2x: dx[n,i,j,:] = dy[n,2i,2j,:] + dy[n,2i,2j+1,:] + dy[n,2i+1,2j,:] + dy[n,2i+1,2j+1,:] */
 int y5_upsample2x_bwd(const void* dy, int32_t dy_pitch, void* dx, int32_t dx_pitch, int32_t batch, int32_t h, int32_t w,
                       int32_t c, int32_t dtype, void* stream);

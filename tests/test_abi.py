@@ -51,6 +51,8 @@ def test_wgrad_and_bn_argument_validation_without_gpu(built_lib):
     assert lib.y5_sppf_bwd_workspace_bytes(2, 20, 20, 128) == 3 * 2 * 20 * 20 * 128 * 4
     assert lib.y5_bn_stats(None, 64, 10, 64, _lib.Y5_F16, None, None) == -1
     assert lib.y5_weight_pack(None, _lib.Y5_F32, 8, 8, 1, None, 8, None, 8, _lib.Y5_F16, None) == -1
+    assert lib.y5_weight_pack_chunk_elems() > 0
+    assert lib.y5_weight_pack_multi(None, None, None, 3, _lib.Y5_F16, None) == -1 and lib.y5_weight_pack_multi(None, None, None, 0, _lib.Y5_F16, None) == 0
 
 
 def test_pre_post_optimizer_argument_validation_without_gpu(built_lib):
@@ -114,7 +116,7 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     """sizeof / offsetof of every struct in the header (compiled by gcc) == the ctypes mirrors in yolov5_b200/_lib.py."""
     mirrors = {"y5_conv_desc": _lib.ConvDesc, "y5_detect_desc": _lib.DetectDesc, "y5_nms_params": _lib.NmsParams,
                "y5_loss_params": _lib.LossParams, "y5_wgrad_desc": _lib.WgradDesc, "y5_letterbox_image": _lib.LetterboxImage,
-               "y5_opt_tensor": _lib.OptTensor}
+               "y5_opt_tensor": _lib.OptTensor, "y5_pack_item": _lib.PackItem}
     structs = _header_structs()
     assert sorted(structs) == sorted(mirrors), (sorted(structs), sorted(mirrors))
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]

@@ -38,7 +38,10 @@ def main():
     dt = torch.float16
     code = _lib.dtype_code(dt)
     print(f"{'rows':>9} {'C':>4} | {'stats':>7} {'fwd':>7} {'bwd_red':>7} {'bwd_app':>7}  us   (GB/s of the pass in brackets)")
-    for hw, c in ((320, 32), (160, 64), (160, 32), (80, 128), (80, 64), (40, 256), (40, 128), (20, 512), (20, 256)):
+    shapes = ((320, 32), (160, 64), (160, 32), (80, 128), (80, 64), (40, 256), (40, 128), (20, 512), (20, 256))
+    if os.environ.get("PROBE_SHAPES") == "m":  # yolov5m's channel widths
+        shapes = ((320, 48), (160, 96), (160, 48), (80, 192), (80, 96), (40, 384), (40, 192), (20, 768), (20, 384))
+    for hw, c in shapes:
         rows = B * hw * hw
         y = torch.randn(rows, c, device=dev).to(dt)
         dz = torch.randn(rows, c, device=dev).to(dt)
@@ -60,6 +63,8 @@ def main():
         nb = rows * c * 2
         print(f"{rows:>9} {c:>4} | {t_stats:7.1f} ({nb / t_stats / 1e3:5.0f}) {t_fwd:7.1f} ({2 * nb / t_fwd / 1e3:5.0f}) {t_bwd:7.1f} ({5 * nb / t_bwd / 1e3:5.0f})",
               flush=True)
+    if os.environ.get("PROBE_BN_ONLY"):
+        return
     print(f"\nwgrad: {'B,H,W':>12} {'cin':>4} {'cout':>4} k s |     us   TFLOP/s")
     for hw, cin, cout, k, s in ((320, 16, 32, 3, 1), (320, 32, 64, 3, 2), (160, 64, 64, 1, 1), (160, 32, 32, 3, 1), (160, 64, 128, 3, 2),
                                 (80, 128, 128, 1, 1), (80, 64, 64, 3, 1), (80, 128, 256, 3, 2), (40, 256, 256, 1, 1), (40, 128, 128, 3, 1),

@@ -101,6 +101,13 @@ class OptTensor(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("fwd", C.c_void_p), ("dgrad", C.c_void_p), ("w_dtype", C.c_int32),
+        ("out_c", C.c_int32), ("in_c", C.c_int32), ("ksize", C.c_int32), ("in_c_pad", C.c_int32), ("out_c_pad", C.c_int32),
+    ]
+
+
 # indices into the fused optimizer's `hyper` array (include/y5b200.h Y5_OPT_*)
 OPT_INV_SCALE, OPT_MAX_NORM, OPT_EMA_DECAY, OPT_EMA_TAU, OPT_EMA_UPDATES, OPT_OUT_NORM, OPT_OUT_SKIPPED, OPT_GROUPS = 0, 1, 2, 3, 4, 5, 6, 8
 
@@ -142,6 +149,8 @@ SIGNATURES = {
     "y5_bn_act_bwd": (_I32, [_P, _I32, _P, _I32, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "y5_col_sum": (_I32, [_P, _I32, _I64, _I32, _I32, _P, _P, _P]),
     "y5_weight_pack": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _I32, _P, _I32, _I32, _P]),
+    "y5_weight_pack_chunk_elems": (_I32, []),
+    "y5_weight_pack_multi": (_I32, [_P, _P, _P, _I32, _I32, _P]),
     "y5_zero_stuff2x": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "y5_loss_fwd_bwd_scaled": (_I32, [C.POINTER(LossParams), C.POINTER(_P), _P, _P, _P, C.POINTER(_P), _P, _P, _I64, _P]),
     "y5_letterbox_max_images": (_I32, []),

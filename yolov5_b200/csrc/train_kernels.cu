@@ -18,36 +18,54 @@
 namespace y5 {
 
 constexpr int kRedThreads = 256;
+constexpr int kUnroll = 4;  // rows a thread has in flight per loop trip (4 x 16 B per operand)
 
 struct RowGeom {
     int cgx;   // channel groups (of 8) handled side by side by one block
     int rows;  // thread rows per block
-    int rpb;   // tensor rows per block: sized so the grid has ~8 blocks per SM (small maps) but at most 1024 rows
+    int rpb;   // tensor rows per block
 };
-constexpr int kUnroll = 4;  // rows per loop trip of the statistics pass; the BN passes take 2 and rely on occupancy
 static inline int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e && atoi(e) > 0 ? atoi(e) : dflt;
 }
-static inline RowGeom row_geom(int channels, long long nrows, int blocks_per_sm) {
-    // tuning knobs (blocks per SM the grids aim for): reductions default 3, elementwise passes default 6
-    static const int red_bps = env_int("Y5_BN_RED_BPS", 3), elt_bps = env_int("Y5_BN_ELT_BPS", 6);
-    blocks_per_sm = blocks_per_sm <= 3 ? red_bps : elt_bps;
+// Block geometry of the row-walking passes.  `reduce` passes end with 2 x (channels of the block) fp64 atomics per block and
+// the L2 retires only ~14 G of those per second (measured: 6400 x 512 statistics took 14.5 us with 400 blocks, 7.9 us with 200),
+// so they want FEW row blocks: at least Y5_BN_RED_MIN_ROWS rows per block, and the block count comes from narrowing the
+// channel span of a block (down to 4 groups = 64 contiguous bytes per row) instead of from shortening it.  Elementwise passes
+// only pay a per-block prologue (per-channel constants), so they keep the widest span and at least two loop trips per thread.
+static inline RowGeom row_geom(int channels, long long nrows, bool reduce, int resident = 4) {
+    // blocks per SM the grids aim for: whole waves of the kernel's residency (4 blocks/SM forward, 3 backward)
+    static const int red_bps = env_int("Y5_BN_RED_BPS", 3), elt_waves = env_int("Y5_BN_ELT_WAVES", 2);
+    const int elt_bps = elt_waves * resident;
+    static const int red_min_rows = env_int("Y5_BN_RED_MIN_ROWS", 512);
     const int cg = channels / 8;
+    const long long target = static_cast<long long>(sm_count()) * (reduce ? red_bps : elt_bps);
+    int cgx = cg >= 32 ? 32 : (cg >= 16 ? 16 : (cg >= 8 ? 8 : (cg >= 4 ? 4 : (cg >= 2 ? 2 : 1))));
     RowGeom g;
-    g.cgx = cg >= 32 ? 32 : (cg >= 16 ? 16 : (cg >= 8 ? 8 : (cg >= 4 ? 4 : (cg >= 2 ? 2 : 1))));
-    g.rows = kRedThreads / g.cgx;
-    const long long gx = (cg + g.cgx - 1) / g.cgx;
-    const long long target = static_cast<long long>(sm_count()) * blocks_per_sm;
-    long long rpb = (nrows * gx + target - 1) / target;
-    const long long quantum = static_cast<long long>(g.rows) * kUnroll;
-    if (rpb < quantum) rpb = quantum;
-    g.rpb = static_cast<int>((rpb + quantum - 1) / quantum * quantum);
+    for (;; cgx >>= 1) {
+        g.cgx = cgx;
+        g.rows = kRedThreads / cgx;
+        const long long gx = (cg + cgx - 1) / cgx;
+        const long long quantum = static_cast<long long>(g.rows) * kUnroll;
+        long long rpb = (nrows * gx + target - 1) / target;
+        const long long floor_rows = reduce ? std::max<long long>(red_min_rows, quantum) : 2 * quantum;
+        if (rpb < floor_rows) rpb = floor_rows;
+        rpb = (rpb + quantum - 1) / quantum * quantum;
+        g.rpb = static_cast<int>(rpb);
+        const long long blocks = gx * ((nrows + rpb - 1) / rpb);
+        if (!reduce || cgx <= 4 || blocks * 5 >= target * 3) break;
+    }
     return g;
 }
 
-__device__ __forceinline__ void load8(const void* base, long long elem_off, bool bf16, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + elem_off);
+__device__ __forceinline__ uint4 ld16(const void* base, long long elem_off) {
+    return *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + elem_off);
+}
+__device__ __forceinline__ void st16(void* base, long long elem_off, const uint4& u) {
+    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + elem_off) = u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, bool bf16, float (&v)[8]) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -56,33 +74,43 @@ __device__ __forceinline__ void load8(const void* base, long long elem_off, bool
         v[2 * i + 1] = f.y;
     }
 }
-__device__ __forceinline__ void store8(void* base, long long elem_off, bool bf16, const float (&v)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&v)[8], bool bf16) {
     uint4 u;
     u.x = pack2(v[0], v[1], bf16);
     u.y = pack2(v[2], v[3], bf16);
     u.z = pack2(v[4], v[5], bf16);
     u.w = pack2(v[6], v[7], bf16);
-    *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + elem_off) = u;
+    return u;
 }
+__device__ __forceinline__ void load8(const void* base, long long elem_off, bool bf16, float (&v)[8]) { unpack8(ld16(base, elem_off), bf16, v); }
+__device__ __forceinline__ void store8(void* base, long long elem_off, bool bf16, const float (&v)[8]) { st16(base, elem_off, pack8(v, bf16)); }
 __device__ __forceinline__ float round_lowp(float x, bool bf16) { return unpack1(pack1(x, bf16), bf16); }
 
-// block-level combine of NV per-thread vectors of 8 channels over the thread rows, then fp64 atomics
+// block-level combine of NV per-thread vectors of 8 channels over the thread rows, then fp64 atomics.  The scratch is
+// [channel-in-group][thread] with a row pitch of 256 + cgx words: stores and the column walk are both bank-conflict free.
 template <int NV>
 __device__ __forceinline__ void block_publish(float (&acc)[NV][8], int cgx, int nrows, int channels, double* const (&dst)[NV]) {
-    __shared__ float red[kRedThreads * 8];
+    __shared__ float red[8 * (kRedThreads + 32)];
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
+    const int pitch = kRedThreads + cgx;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) red[(ty * cgx + tx) * 8 + i] = acc[v][i];
+        for (int i = 0; i < 8; ++i) red[i * pitch + threadIdx.x] = acc[v][i];
         __syncthreads();
-        // thread (tx, ty < 8) sums channel ty of group tx over all rows
+        // thread (tx, ty < 8) sums channel ty of group tx over all thread rows
         if (ty < 8) {
-            float s = 0.f;
-            for (int r = 0; r < nrows; ++r) s += red[(r * cgx + tx) * 8 + ty];
+            const float* col = red + ty * pitch + tx;
+            float s0 = 0.f, s1 = 0.f;
+            int r = 0;
+            for (; r + 1 < nrows; r += 2) {
+                s0 += col[r * cgx];
+                s1 += col[(r + 1) * cgx];
+            }
+            if (r < nrows) s0 += col[r * cgx];
             const int c = (blockIdx.x * cgx + tx) * 8 + ty;
-            if (c < channels) atomicAdd(dst[v] + c, static_cast<double>(s));
+            if (c < channels) atomicAdd(dst[v] + c, static_cast<double>(s0 + s1));
         }
     }
 }
@@ -97,27 +125,28 @@ __global__ void __launch_bounds__(kRedThreads) col_stats_kernel(const void* __re
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     const bool active = cg * 8 < channels;
+    const bool b = bf16 != 0;
     float acc[MODE == 0 ? 2 : 1][8] = {};
     const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
     const long long r1 = min(rows, r0 + rpb);
     if (active)
         for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
-            float v[kUnroll][8];
+            uint4 raw[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const long long rr = r + u * nrows;
-                if (rr < r1) load8(y, rr * pitch + cg * 8, bf16 != 0, v[u]);
-                else
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+                raw[u] = rr < r1 ? ld16(y, rr * pitch + cg * 8) : make_uint4(0u, 0u, 0u, 0u);  // +0.0 in both formats
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u)
+            for (int u = 0; u < kUnroll; ++u) {
+                float v[8];
+                unpack8(raw[u], b, v);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    acc[0][i] += v[u][i];
-                    if (MODE == 0) acc[1][i] = fmaf(v[u][i], v[u][i], acc[1][i]);
+                    acc[0][i] += v[i];
+                    if (MODE == 0) acc[1][i] = fmaf(v[i], v[i], acc[1][i]);
                 }
+            }
         }
     if constexpr (MODE == 0) {
         double* const dst[2] = {ws, ws + channels};
@@ -133,14 +162,21 @@ __global__ void col_sum_finalize_kernel(const double* __restrict__ ws, int chann
     if (c < channels) out[c] = static_cast<float>(ws[c]);
 }
 
-// Per-channel constants of the three passes live in shared memory (4 floats per channel of the block's channel groups):
+// Per-channel constants of the three passes live in shared memory:
 //   a = invstd*gamma, b = beta - mean*a           -> t = round(y*a + b) is the BN output
 //   forward : z = silu(t)
 //   reduce  : xh = y*is + m2 (m2 = -mean*invstd);  du = dz*silu'(t);  sum du, sum du*xh
 //   apply   : dy = du*a + y*c1 + c0  with c1 = -invstd*(dgamma/rows)*a,  c0 = -(dbeta/rows + m2*dgamma/rows)*a
 // which is (du - dbeta/rows - xh*dgamma/rows)*gamma*invstd written so that four constants per channel suffice; keeping
-// them out of registers lets 3-4 blocks share an SM, and that occupancy is what hides the HBM latency of these passes.
-struct ChanConst { float a, b, c, d; };
+// them out of registers lets 3-4 blocks share an SM.  Layout: two float2 tables indexed [channel-in-group * cgx + group] --
+// the threads of a warp own consecutive groups, so every read is one conflict-free wavefront.  (Round 1 kept one 16-byte
+// struct per channel, i.e. a 128-byte stride between the threads of a warp: 16-way bank conflicts on every constant read made
+// shared memory, not HBM, the bound of these passes for layers with >= 64 channels -- 1.7 TB/s at 128 channels vs 3.5 TB/s at 32.)
+struct ChanTables {
+    float2 ab[kRedThreads];
+    float2 cd[kRedThreads];
+};
+__device__ __forceinline__ int chan_slot(int i, int cgx) { return (i & 7) * cgx + (i >> 3); }  // i = channel inside the block's span
 
 __device__ __forceinline__ float act_bwd(float dz, float t, int act, bool bf16) {
     if (!act) return dz;
@@ -148,73 +184,78 @@ __device__ __forceinline__ float act_bwd(float dz, float t, int act, bool bf16) 
     return round_lowp(dz * sg * (1.0f + t * (1.0f - sg)), bf16);
 }
 
-__global__ void __launch_bounds__(kRedThreads, 4) bn_act_fwd_kernel(const void* __restrict__ y, int y_pitch, void* __restrict__ z, int z_pitch,
+template <bool RES>
+__global__ void __launch_bounds__(kRedThreads, RES ? 3 : 4) bn_act_fwd_kernel(const void* __restrict__ y, int y_pitch, void* __restrict__ z, int z_pitch,
                                                                     long long rows, int channels, int bf16, int act, int cgx, int rpb,
                                                                     float* __restrict__ mean, float* __restrict__ invstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                    const double* __restrict__ sums, float eps, float momentum,
-                                                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                                    const void* __restrict__ res, int res_pitch) {
+                                                                    const double* __restrict__ sums, double inv_rows, double unbias, float eps,
+                                                                    float momentum, float* __restrict__ running_mean,
+                                                                    float* __restrict__ running_var, const void* __restrict__ res, int res_pitch) {
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
     griddep_launch_dependents();
-    __shared__ ChanConst cc[256];
+    __shared__ float2 tab[kRedThreads];
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
         const int c = blockIdx.x * cgx * 8 + i;
-        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        float2 k = make_float2(0.f, 0.f);
         if (c < channels) {
             float mu, is;
             if (sums) {  // batch statistics from the column sums of y5_bn_stats (every block derives what it needs; row-block 0 publishes)
-                const double m = sums[c] / static_cast<double>(rows);
-                double var = sums[channels + c] / static_cast<double>(rows) - m * m;
+                const double m = sums[c] * inv_rows;
+                double var = fma(sums[channels + c], inv_rows, -m * m);
                 if (var < 0.0) var = 0.0;
                 mu = static_cast<float>(m);
-                is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+                is = static_cast<float>(rsqrt(var + static_cast<double>(eps)));
                 if (blockIdx.y == 0) {
                     mean[c] = mu;
                     invstd[c] = is;
                     if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
-                    if (running_var) {
-                        const double unbiased = rows > 1 ? var * static_cast<double>(rows) / static_cast<double>(rows - 1) : var;
-                        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-                    }
+                    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(var * unbias);
                 }
             } else {
                 mu = mean[c];
                 is = invstd[c];
             }
-            k.a = is * gamma[c];
-            k.b = beta[c] - mu * k.a;
+            k.x = is * gamma[c];
+            k.y = beta[c] - mu * k.x;
         }
-        cc[i] = k;
+        tab[chan_slot(i, cgx)] = k;
     }
     __syncthreads();
     if (cg * 8 >= channels) return;
     const bool b = bf16 != 0;
-    const ChanConst* my = cc + tx * 8;
+    const float2* kt = tab + tx;  // this thread's 8 channels: kt[i * cgx], one conflict-free wavefront per read
     const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
     const long long r1 = min(rows, r0 + rpb);
-    for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
-        float v[2][8], q[2][8];
-        const bool two = r + nrows < r1;
-        load8(y, r * y_pitch + cg * 8, b, v[0]);
-        if (two) load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
-        if (res) {  // Bottleneck shortcut (models/common.py:181): z = x + SiLU(BN(y)), each term rounded like the reference's add
-            load8(res, r * res_pitch + cg * 8, b, q[0]);
-            if (two) load8(res, (r + nrows) * res_pitch + cg * 8, b, q[1]);
+    for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
+        uint4 yv[kUnroll], qv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long rr = r + u * nrows;
+            if (rr < r1) {
+                yv[u] = ld16(y, rr * y_pitch + cg * 8);
+                if (RES) qv[u] = ld16(res, rr * res_pitch + cg * 8);  // Bottleneck shortcut (models/common.py:181)
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long rr = r + u * nrows;
+            if (rr < r1) {
+                float v[8], q[8];
+                unpack8(yv[u], b, v);
+                if (RES) unpack8(qv[u], b, q);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
-                v[u][i] = act ? __fdividef(t, 1.0f + __expf(-t)) : t;
-                if (res) v[u][i] = round_lowp(v[u][i], b) + q[u][i];
+                for (int i = 0; i < 8; ++i) {
+                    const float2 k = kt[i * cgx];
+                    const float t = round_lowp(fmaf(v[i], k.x, k.y), b);
+                    v[i] = act ? __fdividef(t, 1.0f + __expf(-t)) : t;
+                    if (RES) v[i] = round_lowp(v[i], b) + q[i];  // z = x + SiLU(BN(y)), each term rounded like the reference's add
+                }
+                st16(z, rr * z_pitch + cg * 8, pack8(v, b));
             }
-            store8(z, (r + u * nrows) * z_pitch + cg * 8, b, v[u]);
         }
     }
 }
@@ -226,47 +267,55 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const
                                                                            const float* __restrict__ beta, double* __restrict__ ws) {
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
     griddep_launch_dependents();
-    __shared__ ChanConst cc[256];
+    __shared__ ChanTables tab;
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
         const int c = blockIdx.x * cgx * 8 + i;
-        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        float2 ab = make_float2(0.f, 0.f), cd = make_float2(0.f, 0.f);
         if (c < channels) {
-            k.a = invstd[c] * gamma[c];
-            k.b = beta[c] - mean[c] * k.a;
-            k.c = invstd[c];
-            k.d = -mean[c] * invstd[c];
+            ab.x = invstd[c] * gamma[c];
+            ab.y = beta[c] - mean[c] * ab.x;
+            cd.x = invstd[c];
+            cd.y = -mean[c] * invstd[c];
         }
-        cc[i] = k;
+        tab.ab[chan_slot(i, cgx)] = ab;
+        tab.cd[chan_slot(i, cgx)] = cd;
     }
     __syncthreads();
     const bool active = cg * 8 < channels;
     const bool b = bf16 != 0;
     float acc[2][8] = {};
     if (active) {
-        const ChanConst* my = cc + tx * 8;
+        const float2* kab = tab.ab + tx;
+        const float2* kcd = tab.cd + tx;
         const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
         const long long r1 = min(rows, r0 + rpb);
-        for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
-            float v[2][8], g[2][8];
-            const bool two = r + nrows < r1;
-            load8(y, r * y_pitch + cg * 8, b, v[0]);
-            load8(dz, r * dz_pitch + cg * 8, b, g[0]);
-            if (two) {
-                load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
-                load8(dz, (r + nrows) * dz_pitch + cg * 8, b, g[1]);
+        for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
+            uint4 yv[kUnroll], gv[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const long long rr = r + u * nrows;
+                if (rr < r1) {
+                    yv[u] = ld16(y, rr * y_pitch + cg * 8);
+                    gv[u] = ld16(dz, rr * dz_pitch + cg * 8);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !two) break;
+            for (int u = 0; u < kUnroll; ++u) {
+                if (r + u * nrows < r1) {
+                    float v[8], g[8];
+                    unpack8(yv[u], b, v);
+                    unpack8(gv[u], b, g);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
-                    const float du = act_bwd(g[u][i], t, act, b);
-                    acc[0][i] += du;
-                    acc[1][i] = fmaf(du, fmaf(v[u][i], my[i].c, my[i].d), acc[1][i]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 ab = kab[i * cgx], cd = kcd[i * cgx];
+                        const float t = round_lowp(fmaf(v[i], ab.x, ab.y), b);
+                        const float du = act_bwd(g[i], t, act, b);
+                        acc[0][i] += du;
+                        acc[1][i] = fmaf(du, fmaf(v[i], cd.x, cd.y), acc[1][i]);
+                    }
                 }
             }
         }
@@ -284,14 +333,14 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
                                                                           float* __restrict__ dbeta) {
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
     griddep_launch_dependents();
-    __shared__ ChanConst cc[256];
+    __shared__ ChanTables tab;
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     const float inv_rows = 1.0f / static_cast<float>(rows);
     for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
         const int c = blockIdx.x * cgx * 8 + i;
-        ChanConst k{0.f, 0.f, 0.f, 0.f};
+        float2 ab = make_float2(0.f, 0.f), cd = make_float2(0.f, 0.f);
         if (c < channels) {
             const float db = static_cast<float>(ws[c]), dg = static_cast<float>(ws[channels + c]);
             if (blockIdx.y == 0) {
@@ -299,38 +348,47 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
                 dgamma[c] = dg;
             }
             const float is = invstd[c], m2 = -mean[c] * is;
-            k.a = is * gamma[c];
-            k.b = beta[c] - mean[c] * k.a;
-            k.c = -is * (dg * inv_rows) * k.a;
-            k.d = -(db * inv_rows + m2 * (dg * inv_rows)) * k.a;
+            ab.x = is * gamma[c];
+            ab.y = beta[c] - mean[c] * ab.x;
+            cd.x = -is * (dg * inv_rows) * ab.x;
+            cd.y = -(db * inv_rows + m2 * (dg * inv_rows)) * ab.x;
         }
-        cc[i] = k;
+        tab.ab[chan_slot(i, cgx)] = ab;
+        tab.cd[chan_slot(i, cgx)] = cd;
     }
     __syncthreads();
     if (cg * 8 >= channels) return;
     const bool b = bf16 != 0;
-    const ChanConst* my = cc + tx * 8;
+    const float2* kab = tab.ab + tx;
+    const float2* kcd = tab.cd + tx;
     const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
     const long long r1 = min(rows, r0 + rpb);
-    for (long long r = r0 + ty; r < r1; r += 2 * nrows) {
-        float v[2][8], g[2][8];
-        const bool two = r + nrows < r1;
-        load8(y, r * y_pitch + cg * 8, b, v[0]);
-        load8(dz, r * dz_pitch + cg * 8, b, g[0]);
-        if (two) {
-            load8(y, (r + nrows) * y_pitch + cg * 8, b, v[1]);
-            load8(dz, (r + nrows) * dz_pitch + cg * 8, b, g[1]);
+    for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
+        uint4 yv[kUnroll], gv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long rr = r + u * nrows;
+            if (rr < r1) {
+                yv[u] = ld16(y, rr * y_pitch + cg * 8);
+                gv[u] = ld16(dz, rr * dz_pitch + cg * 8);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long rr = r + u * nrows;
+            if (rr < r1) {
+                float v[8], g[8];
+                unpack8(yv[u], b, v);
+                unpack8(gv[u], b, g);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float t = round_lowp(fmaf(v[u][i], my[i].a, my[i].b), b);
-                const float du = act_bwd(g[u][i], t, act, b);
-                v[u][i] = fmaf(du, my[i].a, fmaf(v[u][i], my[i].c, my[i].d));
+                for (int i = 0; i < 8; ++i) {
+                    const float2 ab = kab[i * cgx], cd = kcd[i * cgx];
+                    const float t = round_lowp(fmaf(v[i], ab.x, ab.y), b);
+                    const float du = act_bwd(g[i], t, act, b);
+                    v[i] = fmaf(du, ab.x, fmaf(v[i], cd.x, cd.y));
+                }
+                st16(dy, rr * dy_pitch + cg * 8, pack8(v, b));
             }
-            store8(dy, (r + u * nrows) * dy_pitch + cg * 8, b, v[u]);
         }
     }
 }
@@ -362,6 +420,30 @@ __device__ __forceinline__ float load_w(const void* w, long long i, int src_dtyp
     if (src_dtype == Y5_F32) return static_cast<const float*>(w)[i];
     return unpack1(static_cast<const uint16_t*>(w)[i], src_dtype == Y5_BF16);
 }
+// element i of the concatenated [forward packing | data-gradient packing] of one OIHW filter
+__device__ __forceinline__ void pack_elem(const void* __restrict__ w, int src_dtype, int cout, int cin, int k, uint16_t* __restrict__ fwd,
+                                          int ci_pad, uint16_t* __restrict__ dgrad, int co_pad, bool bf16, long long n_fwd, long long i) {
+    if (i < n_fwd) {
+        const int ci = static_cast<int>(i % ci_pad);
+        long long t = i / ci_pad;
+        const int s_ = static_cast<int>(t % k);
+        t /= k;
+        const int r = static_cast<int>(t % k);
+        const int co = static_cast<int>(t / k);
+        const float v = ci < cin ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + r) * k + s_, src_dtype) : 0.f;
+        fwd[i] = pack1(v, bf16);
+    } else {
+        const long long j = i - n_fwd;
+        const int co = static_cast<int>(j % co_pad);
+        long long t = j / co_pad;
+        const int s_ = static_cast<int>(t % k);
+        t /= k;
+        const int r = static_cast<int>(t % k);
+        const int ci = static_cast<int>(t / k);
+        const float v = co < cout ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s_), src_dtype) : 0.f;
+        dgrad[j] = pack1(v, bf16);
+    }
+}
 __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, int cout, int cin, int k, uint16_t* __restrict__ fwd, int ci_pad,
                                    uint16_t* __restrict__ dgrad, int co_pad, int bf16) {
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
@@ -369,30 +451,25 @@ __global__ void weight_pack_kernel(const void* __restrict__ w, int src_dtype, in
     const long long n_fwd = fwd ? static_cast<long long>(cout) * k * k * ci_pad : 0;
     const long long n_dg = dgrad ? static_cast<long long>(cin) * k * k * co_pad : 0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_fwd + n_dg;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        if (i < n_fwd) {
-            const int ci = static_cast<int>(i % ci_pad);
-            long long t = i / ci_pad;
-            const int s_ = static_cast<int>(t % k);
-            t /= k;
-            const int r = static_cast<int>(t % k);
-            const int co = static_cast<int>(t / k);
-            const float v = ci < cin ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + r) * k + s_, src_dtype) : 0.f;
-            fwd[i] = pack1(v, bf16 != 0);
-        } else {
-            const long long j = i - n_fwd;
-            const int co = static_cast<int>(j % co_pad);
-            long long t = j / co_pad;
-            const int s_ = static_cast<int>(t % k);
-            t /= k;
-            const int r = static_cast<int>(t % k);
-            const int ci = static_cast<int>(t / k);
-            const float v = co < cout ? load_w(w, ((static_cast<long long>(co) * cin + ci) * k + (k - 1 - r)) * k + (k - 1 - s_), src_dtype) : 0.f;
-            dgrad[j] = pack1(v, bf16 != 0);
-        }
-    }
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        pack_elem(w, src_dtype, cout, cin, k, fwd, ci_pad, dgrad, co_pad, bf16 != 0, n_fwd, i);
 }
-
+// every filter of a model in ONE launch (the per-step re-packing of the fp32 master weights): block b works on piece
+// chunk_index[b] (kPackChunk elements) of item chunk_item[b]
+constexpr int kPackChunk = 8192;
+__global__ void __launch_bounds__(256) weight_pack_multi_kernel(const y5_pack_item* __restrict__ items, const int32_t* __restrict__ chunk_item,
+                                                                const int32_t* __restrict__ chunk_index, int bf16) {
+    griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
+    griddep_launch_dependents();
+    const y5_pack_item it = items[chunk_item[blockIdx.x]];
+    const long long n_fwd = it.fwd ? static_cast<long long>(it.out_c) * it.ksize * it.ksize * it.in_c_pad : 0;
+    const long long n_dg = it.dgrad ? static_cast<long long>(it.in_c) * it.ksize * it.ksize * it.out_c_pad : 0;
+    const long long i0 = static_cast<long long>(chunk_index[blockIdx.x]) * kPackChunk;
+    const long long i1 = min(n_fwd + n_dg, i0 + kPackChunk);
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+        pack_elem(it.w, it.w_dtype, it.out_c, it.in_c, it.ksize, static_cast<uint16_t*>(it.fwd), it.in_c_pad, static_cast<uint16_t*>(it.dgrad),
+                  it.out_c_pad, bf16 != 0, n_fwd, i);
+}
 
 // eval-mode BatchNorm folded into the conv weights + K-major packing, one launch (reference utils/torch_utils.py:224-254):
 // scale = gamma / sqrt(var + eps) in fp32 (same operation order as torch's expression), W' = W * scale rounded once to the
@@ -541,7 +618,7 @@ extern "C" Y5_API int y5_bn_stats(const void* y, int32_t pitch, int64_t rows, in
     if (int e = check_view(y, pitch, channels, "bn_stats")) return e;
     if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "bn_stats: dtype must be fp16 or bf16");
     if (!workspace || rows <= 0) return set_error(Y5_E_INVALID, "bn_stats: bad argument");
-    const RowGeom g = row_geom(channels, rows, 3);
+    const RowGeom g = row_geom(channels, rows, true);
     count_launch();
     launch_pdl(col_stats_kernel<0>, row_grid(g, channels, rows), dim3(kRedThreads), 0, static_cast<cudaStream_t>(stream), 
         y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb, static_cast<double*>(workspace));
@@ -555,7 +632,7 @@ extern "C" Y5_API int y5_col_sum(const void* y, int32_t pitch, int64_t rows, int
     if (!out || !workspace || rows <= 0) return set_error(Y5_E_INVALID, "col_sum: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(workspace, 0, static_cast<size_t>(channels) * sizeof(double), st);
-    const RowGeom g = row_geom(channels, rows, 3);
+    const RowGeom g = row_geom(channels, rows, true);
     count_launch(2);
     launch_pdl(col_stats_kernel<1>, row_grid(g, channels, rows), dim3(kRedThreads), 0, st, y, pitch, rows, channels, dtype == Y5_BF16, g.cgx, g.rpb,
                                                                               static_cast<double*>(workspace));
@@ -573,10 +650,12 @@ extern "C" Y5_API int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int
     if (!mean || !invstd || !gamma || !beta || rows <= 0) return set_error(Y5_E_INVALID, "bn_act_fwd: bad argument");
     if (residual)
         if (int e = check_view(residual, res_pitch, channels, "bn_act_fwd residual")) return e;
-    const RowGeom g = row_geom(channels, rows, 6);
+    const RowGeom g = row_geom(channels, rows, false, residual ? 3 : 4);
+    const double inv_rows = 1.0 / static_cast<double>(rows);
+    const double unbias = rows > 1 ? static_cast<double>(rows) / static_cast<double>(rows - 1) : 1.0;
     count_launch();
-    launch_pdl(bn_act_fwd_kernel, row_grid(g, channels, rows), dim3(kRedThreads), 0, static_cast<cudaStream_t>(stream), 
-        y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<const double*>(sums), eps, momentum,
+    launch_pdl(residual ? bn_act_fwd_kernel<true> : bn_act_fwd_kernel<false>, row_grid(g, channels, rows), dim3(kRedThreads), 0, static_cast<cudaStream_t>(stream), 
+        y, y_pitch, z, z_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<const double*>(sums), inv_rows, unbias, eps, momentum,
         running_mean, running_var, residual, res_pitch);
     return launch_status("bn_act_fwd");
 }
@@ -591,7 +670,7 @@ extern "C" Y5_API int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* 
     if (!mean || !invstd || !gamma || !beta || !dgamma || !dbeta || !workspace || rows <= 0)
         return set_error(Y5_E_INVALID, "bn_act_bwd: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const RowGeom g = row_geom(channels, rows, 3), ga = row_geom(channels, rows, 6);
+    const RowGeom g = row_geom(channels, rows, true), ga = row_geom(channels, rows, false, 3);
     const dim3 grid = row_grid(g, channels, rows);
     count_launch(2);
     launch_pdl(bn_act_bwd_reduce_kernel, grid, dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd,
@@ -631,6 +710,19 @@ extern "C" Y5_API int y5_weight_pack(const void* w, int32_t w_dtype, int32_t out
     return launch_status("weight_pack");
 }
 
+
+extern "C" Y5_API int32_t y5_weight_pack_chunk_elems(void) { return kPackChunk; }
+
+extern "C" Y5_API int y5_weight_pack_multi(const y5_pack_item* items, const int32_t* chunk_item, const int32_t* chunk_index, int32_t n_chunks,
+                                           int32_t dtype, void* stream) {
+    if (n_chunks == 0) return 0;
+    if (!items || !chunk_item || !chunk_index || n_chunks < 0) return set_error(Y5_E_INVALID, "weight_pack_multi: bad argument");
+    if (dtype != Y5_F16 && dtype != Y5_BF16) return set_error(Y5_E_UNSUPPORTED, "weight_pack_multi: packed dtype must be fp16 or bf16");
+    count_launch();
+    launch_pdl(weight_pack_multi_kernel, dim3(static_cast<unsigned>(n_chunks)), dim3(256), 0, static_cast<cudaStream_t>(stream), items, chunk_item,
+               chunk_index, dtype == Y5_BF16);
+    return launch_status("weight_pack_multi");
+}
 
 extern "C" Y5_API int y5_fold_pack(const void* w, int32_t w_dtype, int32_t out_c, int32_t in_c, int32_t kh, int32_t kw, const void* conv_bias,
                                    const void* gamma, const void* beta, const void* mean, const void* var, int32_t bn_dtype, float eps,

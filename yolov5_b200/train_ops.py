@@ -70,10 +70,17 @@ def _zero_bias(n: int, device) -> torch.Tensor:
     return t
 
 
+_block_k_cache: dict = {}
+
+
 def _block_k(cin: int, cout: int, m_rows: int) -> int:
-    bk = C.c_int32()
-    _lib.check(_lib.lib().y5_conv_pick(cin, cout, m_rows, C.byref(bk), None), "conv_pick")
-    return bk.value
+    key = (cin, cout, m_rows)
+    v = _block_k_cache.get(key)
+    if v is None:  # a pure function of the shape: one library call per distinct layer shape, not two per layer per step
+        bk = C.c_int32()
+        _lib.check(_lib.lib().y5_conv_pick(cin, cout, m_rows, C.byref(bk), None), "conv_pick")
+        v = _block_k_cache[key] = bk.value
+    return v
 
 
 def pack_weights(w: torch.Tensor, dtype: torch.dtype, m_rows: int, want_fwd: bool = True, want_dgrad: bool = False):
@@ -97,6 +104,113 @@ def pack_weights(w: torch.Tensor, dtype: torch.dtype, m_rows: int, want_fwd: boo
     _lib.check(lib.y5_weight_pack(w.data_ptr(), _lib.dtype_code(w.dtype), o, i, k, fwd.data_ptr() if fwd is not None else None, ipad,
                                   dg.data_ptr() if dg is not None else None, opad, _lib.dtype_code(dtype), _st(w.device)), "weight_pack")
     return fwd, dg, bk_f, bk_d
+
+
+class _PackEntry:
+    __slots__ = ("weight", "wptr", "fwd", "dg", "ipad", "opad", "bk_f", "bk_d", "epoch")
+
+
+class PackPlan:
+    """The per-step re-packing of a model's fp32 master weights as ONE launch (y5_weight_pack_multi) into persistent buffers.
+
+    The first training forward packs layer by layer (pack_weights) and registers every filter here together with the buffers
+    it packed into; from the next forward on, `begin()` converts all registered filters in one launch before the first layer
+    runs, and the layers just look their buffers up -- 1 launch and 1 library call per step instead of ~80, no allocations.
+    The buffers are overwritten by the next forward's launch, which is stream-ordered after the backward that read them."""
+
+    def __init__(self, device, dtype):
+        self.device, self.dtype = device, dtype
+        self.entries: dict = {}
+        self.dirty = False
+        self.epoch = 0
+        self.table = None  # (items, chunk_item, chunk_index, n_chunks) in device memory
+        self.keep: list = []  # replaced buffers stay alive: a captured CUDA graph may still write to them
+
+    def __deepcopy__(self, memo):  # copy.deepcopy(model) (ModelEMA): the copy has other parameters, it starts an empty plan
+        return PackPlan(self.device, self.dtype)
+
+    def begin(self):
+        """Start of a training forward: one launch packs every registered filter from the current master weights."""
+        self.epoch += 1
+        if self.dirty or self.table is None:
+            if torch.cuda.is_current_stream_capturing():
+                return  # no host-to-device table upload inside a capture: this forward packs layer by layer
+            self._build()
+        if self.table is None:
+            return
+        items, ci, cx, n, ents = self.table
+        with _lib.on(self.device):
+            _lib.check(_lib.lib().y5_weight_pack_multi(items.data_ptr(), ci.data_ptr(), cx.data_ptr(), n, _lib.dtype_code(self.dtype),
+                                                       _st(self.device)), "weight_pack_multi")
+        for e in ents:
+            e.epoch = self.epoch
+
+    def _build(self):
+        ents = [e for e in self.entries.values() if e.wptr == e.weight.data_ptr()]
+        self.dirty = False
+        if not ents:
+            self.table = None
+            return
+        chunk = int(_lib.lib().y5_weight_pack_chunk_elems())
+        arr = (_lib.PackItem * len(ents))()
+        ci, cx = [], []
+        for t, e in enumerate(ents):
+            o, i, k, _ = e.weight.shape
+            it = arr[t]
+            it.w, it.fwd, it.dgrad = e.wptr, e.fwd.data_ptr(), (e.dg.data_ptr() if e.dg is not None else None)
+            it.w_dtype = _lib.dtype_code(e.weight.dtype)
+            it.out_c, it.in_c, it.ksize, it.in_c_pad, it.out_c_pad = o, i, k, e.ipad, e.opad
+            total = o * k * k * e.ipad + (i * k * k * e.opad if e.dg is not None else 0)
+            n = (total + chunk - 1) // chunk
+            ci += [t] * n
+            cx += list(range(n))
+        items = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        self.table = (items, torch.tensor(ci, dtype=torch.int32, device=self.device), torch.tensor(cx, dtype=torch.int32, device=self.device),
+                      len(ci), ents)
+
+    def lookup(self, weight, bk_f, bk_d, need_dx):
+        """(fwd, dgrad) buffers holding THIS forward's packing of `weight`, or None (not registered / not packed this forward /
+        another geometry)."""
+        e = self.entries.get(id(weight))
+        if (e is None or e.epoch != self.epoch or e.weight is not weight or e.wptr != weight.data_ptr() or e.bk_f != bk_f
+                or (need_dx and (e.dg is None or e.bk_d != bk_d))):
+            return None
+        return e.fwd, e.dg
+
+    def register(self, weight, fwd, dg, ipad, opad, bk_f, bk_d):
+        if not weight.is_contiguous() or weight.device != self.device or fwd.dtype != self.dtype:
+            return
+        old = self.entries.get(id(weight))
+        if old is not None:
+            self.keep += [old.fwd, old.dg]
+        e = _PackEntry()
+        e.weight, e.wptr, e.fwd, e.dg, e.ipad, e.opad, e.bk_f, e.bk_d, e.epoch = weight, weight.data_ptr(), fwd, dg, ipad, opad, bk_f, bk_d, -1
+        self.entries[id(weight)] = e
+        self.dirty = True
+
+    def tensors(self):
+        """everything a captured graph's pack launch touches (GraphedTrainStep keeps these alive)"""
+        out = list(self.keep)
+        for e in self.entries.values():
+            out += [e.fwd, e.dg]
+        if self.table is not None:
+            out += list(self.table[:3])
+        return out
+
+
+_cur_plan: PackPlan | None = None  # the plan of the forward_train that is running (None: layers pack for themselves)
+
+
+def pack_plan_enabled() -> bool:
+    return os.environ.get("Y5_TRAIN_PACK_PLAN", "1") != "0"
+
+
+def pack_plan(model, dtype, device) -> PackPlan:
+    plans = model.__dict__.setdefault("_y5_pack_plans", {})
+    key = (str(device), dtype)
+    if key not in plans:
+        plans[key] = PackPlan(device, dtype)
+    return plans[key]
 
 
 def conv_packed(x: torch.Tensor, x_pitch: int, wp: torch.Tensor, block_k: int, bias32: torch.Tensor | None, cout: int, k: int, s: int, p: int,
@@ -314,7 +428,19 @@ class _ConvBnAct(torch.autograd.Function):
             bsz, _, h, w_ = x.shape
             m_rows = bsz * ((h + 2 * pe - ke) // se + 1) * ((w_ + 2 * pe - ke) // se + 1)
             need_dx = ctx.needs_input_grad[0] and not stem
-            wp, wp_dg, bk_f, bk_d = pack_weights(w_eff, x.dtype, m_rows, True, need_dx)
+            hit = None
+            if _cur_plan is not None and not stem and _cur_plan.dtype == x.dtype:
+                bk_f = _block_k(w_eff.shape[1], w_eff.shape[0], m_rows)
+                bk_d = _block_k(w_eff.shape[0], w_eff.shape[1], m_rows) if need_dx else 0
+                hit = _cur_plan.lookup(weight, bk_f, bk_d, need_dx)
+            if hit is not None:  # packed by this forward's y5_weight_pack_multi launch
+                wp, wp_dg = hit
+                if not need_dx:
+                    wp_dg = None
+            else:
+                wp, wp_dg, bk_f, bk_d = pack_weights(w_eff, x.dtype, m_rows, True, need_dx)
+                if _cur_plan is not None and not stem and _cur_plan.dtype == x.dtype and isinstance(weight, torch.nn.Parameter):
+                    _cur_plan.register(weight, wp, wp_dg, wp.shape[3], wp_dg.shape[3] if wp_dg is not None else 0, bk_f, bk_d)
             y = conv_packed(x, xp, wp, bk_f, None, w_eff.shape[0], ke, se, pe, act=False)
         b, c, ho, wo = y.shape
         rows = b * ho * wo
@@ -611,17 +737,24 @@ def forward_train(model, img: torch.Tensor):
     if not (isinstance(first, mc.Conv) and first.conv.kernel_size[0] == 6 and first.conv.stride[0] == 2 and first.conv.padding[0] == 2
             and first.conv.in_channels == 3):
         raise NotImplementedError("y5b200: the first layer must be the YOLOv5 v6 stem Conv(3, c, 6, 2, 2)")
-    ys = []
-    x = None
     # every op below picks its dtype explicitly; autocast's own casting rules must not touch the glue ops
+    global _cur_plan
     with torch.autocast("cuda", enabled=False):
         _arena.reset(img.device)
-        for i, m in enumerate(layers):
-            if i == 0:
-                x = conv_module(m, stem_input(img, dt), stem=2 if stem_wide_enabled() else 1)
-            else:
-                if m.f != -1:
-                    x = ys[m.f] if isinstance(m.f, int) else [x if j == -1 else ys[j] for j in m.f]
-                x = _run(m, x, dt)
-            ys.append(x if i in model.save else None)
+        _cur_plan = pack_plan(model, dt, img.device) if pack_plan_enabled() else None
+        try:
+            if _cur_plan is not None:
+                _cur_plan.begin()  # every registered filter -> forward / data-gradient packings, one launch
+            ys = []
+            x = None
+            for i, m in enumerate(layers):
+                if i == 0:
+                    x = conv_module(m, stem_input(img, dt), stem=2 if stem_wide_enabled() else 1)
+                else:
+                    if m.f != -1:
+                        x = ys[m.f] if isinstance(m.f, int) else [x if j == -1 else ys[j] for j in m.f]
+                    x = _run(m, x, dt)
+                ys.append(x if i in model.save else None)
+        finally:
+            _cur_plan = None
     return x

@@ -365,7 +365,10 @@ class GraphedTrainStep:
     `optimizer.param_groups` at every call (uploaded through a pinned buffer the captured copy node reads at replay time), so
     warm-up and schedulers work.  Shapes are fixed at construction: `batch` uint8 images of `size` and up to `max_targets`
     label rows; shorter label tensors are padded with zero-size boxes, which build_targets can never match (the anchor ratio
-    test of utils/loss.py:219 fails for w = h = 0).  Single process only (DDP's bucketed all-reduce hooks are not captured).
+    test of utils/loss.py:219 fails for w = h = 0).  Data parallel: pass an optimizer on which `data_parallel(model)` was called
+    -- its one NCCL all-reduce of the packed gradient arena is captured with the rest of the step (every rank constructs and
+    calls the object in lock-step; the loss is multiplied by the world size like train.py:405).  A model wrapped in
+    DistributedDataParallel is not capturable (autograd hooks, buckets).
 
         opt = smart_optimizer(model, "SGD", lr, momentum, decay); ema = ModelEMA(model)
         step = GraphedTrainStep(model, ComputeLoss(model), opt, batch=16, size=640, ema=ema)
@@ -387,11 +390,17 @@ class GraphedTrainStep:
         self.optimizer, self.max_norm = optimizer, max_norm
         self.scaler = torch.amp.GradScaler("cuda", init_scale=init_scale, enabled=amp_dtype == torch.float16)
         scaler = self.scaler
+        if isinstance(model, (nn.parallel.DataParallel, nn.parallel.DistributedDataParallel)):
+            raise TypeError("GraphedTrainStep: pass the plain module; for data parallel use FusedSGD.data_parallel(model), whose single "
+                            "all-reduce is capturable")
+        world = optimizer._dp[1] if optimizer._dp is not None else 1
 
         def step():
             with torch.autocast("cuda", dtype=amp_dtype):
                 pred = model(self.img)
             loss, items = compute_loss(pred, self.tgt)
+            if world > 1:
+                loss = loss * world  # train.py:405: the all-reduce averages over ranks, the reference rescales
             scaler.scale(loss).backward()
             optimizer.fused_step(scaler=scaler, max_norm=max_norm, ema=ema, model=model)
             optimizer.zero_grad(set_to_none=True)  # gradients return to the graph's private pool: same addresses at every replay
@@ -415,13 +424,15 @@ class GraphedTrainStep:
         for g, lr in zip(optimizer.param_groups, lrs):
             g["lr"] = lr
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with a process group alive, NCCL's watchdog thread issues CUDA calls of its own: only this thread's calls belong to the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if world > 1 else "global"):
             step()
         # the capture baked in the address of the BN-sum arena (allocated during warm-up, outside the graph's pool): keep it
         # alive even if a later eager forward of another shape makes the arena grow
         from .. import train_ops
 
         self._arena_buf = train_ops._arena.buf
+        self._pack_plans = list(model.__dict__.get("_y5_pack_plans", {}).values())  # persistent packed-weight buffers + tables
         # undo what warm-up and capture touched: weights are unchanged (lr 0 / capture does not execute), BN running statistics
         # and batch counters, momentum buffers, the EMA and its counter, the loss scale
         model.load_state_dict(state)
