@@ -232,7 +232,7 @@ def test_conv_layer_train_forward_backward(cuda, k, s, dtype):
     assert int(m.bn.num_batches_tracked) == 1
 
 
-def _ref_train_step(cfg, sd, img, targets, dev, autocast_dtype):
+def _ref_train_step(cfg, sd, img, targets, dev, autocast_dtype, backward=True):
     """torch reference of one training forward/backward (oracle model with batch-stat BN + oracle loss)."""
     params = {k: v.to(dev).clone().requires_grad_(v.is_floating_point() and "running" not in k and "anchors" not in k) for k, v in sd.items()}
     x = img.to(dev).float() / 255 if img.dtype == torch.uint8 else img.to(dev).float()
@@ -240,6 +240,8 @@ def _ref_train_step(cfg, sd, img, targets, dev, autocast_dtype):
     with ctx:
         p = model_ref.forward(cfg, params, x, training=True, bn_batch_stats=True)
     loss, items = loss_ref.compute_loss([q.float().cpu() for q in p], targets, sd["model.24.anchors"], HYP_SCRATCH_LOW)  # CPU oracle
+    if not backward:
+        return [q.detach() for q in p], loss.detach(), {}
     loss.backward()
     grads = {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
     return [q.detach() for q in p], loss.detach(), grads
@@ -278,14 +280,15 @@ def test_model_training_step_vs_oracle_amp_yardstick(cuda, name, shape, dtype):
     # The loss of ONE sample is one draw of low-precision rounding noise for the engine and for torch-AMP alike: three equally
     # valid block geometries of the BN-statistics reduction (fp32 partial sums in another order, mean / invstd moving in the 7th
     # digit) gave |loss - loss32| = 0.0207, < 0.0157 and < 0.0157 on the bf16 sample where AMP's own draw is 0.0089.  So the
-    # loss is judged like a distribution: RMS error over six image batches, engine vs AMP, same 1.5x + 1e-3 bound as before.
+    # loss is judged like a distribution: RMS error over six image batches, engine vs AMP, same 1.5x + 1e-3 bound as before
+    # (measured: bf16 yolov5n 0.0129 vs 0.0076, fp16 yolov5n 0.0013 vs 0.0010, fp16 yolov5m 0.0032 vs 0.0044).
     mine, amp, ref = [abs(float(loss) - float(loss32))], [abs(float(lossamp) - float(loss32))], [abs(float(loss32))]
     for extra in (122, 222, 322, 422, 522):
         ge = torch.Generator().manual_seed(extra)
         img_e = (torch.rand(*shape, generator=ge) * 255).to(torch.uint8)
-        _, l32_e, _ = _ref_train_step(cfg, sd, img_e, targets, cuda, None)
-        _, lamp_e, _ = _ref_train_step(cfg, sd, img_e, targets, cuda, dtype)
-        with torch.autocast("cuda", dtype=dtype):
+        _, l32_e, _ = _ref_train_step(cfg, sd, img_e, targets, cuda, None, backward=False)
+        _, lamp_e, _ = _ref_train_step(cfg, sd, img_e, targets, cuda, dtype, backward=False)
+        with torch.no_grad(), torch.autocast("cuda", dtype=dtype):
             p_e = m(img_e.to(cuda))
         l_e, _ = compute_loss(p_e, targets.to(cuda))
         mine.append(abs(float(l_e) - float(l32_e)))

@@ -36,8 +36,9 @@ static inline int env_int(const char* name, int dflt) {
 // only pay a per-block prologue (per-channel constants), so they keep the widest span and at least two loop trips per thread.
 static inline RowGeom row_geom(int channels, long long nrows, bool reduce, int resident = 4) {
     // blocks per SM the grids aim for: whole waves of the kernel's residency (4 blocks/SM forward, 3 backward)
-    static const int red_bps = env_int("Y5_BN_RED_BPS", 3), elt_waves = env_int("Y5_BN_ELT_WAVES", 2);
+    static const int red_env = env_int("Y5_BN_RED_BPS", 0), elt_waves = env_int("Y5_BN_ELT_WAVES", 2);
     const int elt_bps = elt_waves * resident;
+    const int red_bps = red_env ? red_env : resident;  // reductions: one wave
     static const int red_min_rows = env_int("Y5_BN_RED_MIN_ROWS", 512);
     const int cg = channels / 8;
     const long long target = static_cast<long long>(sm_count()) * (reduce ? red_bps : elt_bps);
@@ -260,11 +261,16 @@ __global__ void __launch_bounds__(kRedThreads, RES ? 3 : 4) bn_act_fwd_kernel(co
     }
 }
 
-__global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
-                                                                           int dz_pitch, long long rows, int channels, int bf16, int act,
+// U rows in flight per thread.  This pass is bound by its instruction stream (exp + reciprocal + ~18 more per element), not by
+// HBM: the constants of a channel pair are read once per loop trip and used for all U rows, and the loop nest is
+// channel-pair-major so that nothing but the raw 16-byte words of the U rows stays live across it.
+template <int U, bool BF16, bool ACT>
+__global__ void __launch_bounds__(kRedThreads, U == 4 ? 2 : 3) bn_act_bwd_reduce_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
+                                                                           int dz_pitch, long long rows, int channels,
                                                                            int cgx, int rpb, const float* __restrict__ mean,
                                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                           const float* __restrict__ beta, double* __restrict__ ws) {
+                                                                           const float* __restrict__ beta, double* __restrict__ ws,
+                                                                           void* __restrict__ du_out, int du_pitch) {
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
     griddep_launch_dependents();
     __shared__ ChanTables tab;
@@ -285,36 +291,59 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const
     }
     __syncthreads();
     const bool active = cg * 8 < channels;
-    const bool b = bf16 != 0;
+    constexpr bool b = BF16;
     float acc[2][8] = {};
     if (active) {
         const float2* kab = tab.ab + tx;
         const float2* kcd = tab.cd + tx;
         const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
-        const long long r1 = min(rows, r0 + rpb);
-        for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
-            uint4 yv[kUnroll], gv[kUnroll];
+        const int n_here = static_cast<int>(min(rows - r0, static_cast<long long>(rpb)));  // rows of this block
+        // block-relative 32-bit element offsets (rpb * pitch < 2^31): one 64-bit base per tensor instead of 64-bit row arithmetic
+        const uint16_t* yb = static_cast<const uint16_t*>(y) + (r0 * y_pitch + cg * 8);
+        const uint16_t* gb = static_cast<const uint16_t*>(dz) + (r0 * dz_pitch + cg * 8);
+        uint16_t* ob = du_out ? static_cast<uint16_t*>(du_out) + (r0 * du_pitch + cg * 8) : nullptr;
+        for (int r = ty; r < n_here; r += U * nrows) {
+            {
+                constexpr int h = 0;
+                uint4 yv[U], gv[U];
+                uint32_t duw[U][4];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const long long rr = r + u * nrows;
-                if (rr < r1) {
-                    yv[u] = ld16(y, rr * y_pitch + cg * 8);
-                    gv[u] = ld16(dz, rr * dz_pitch + cg * 8);
+                for (int u = 0; u < U; ++u) {
+                    const int rr = r + (h + u) * nrows;
+                    if (rr < n_here) {
+                        yv[u] = *reinterpret_cast<const uint4*>(yb + static_cast<uint32_t>(rr) * static_cast<uint32_t>(y_pitch));
+                        gv[u] = *reinterpret_cast<const uint4*>(gb + static_cast<uint32_t>(rr) * static_cast<uint32_t>(dz_pitch));
+                    }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (r + u * nrows < r1) {
-                    float v[8], g[8];
-                    unpack8(yv[u], b, v);
-                    unpack8(gv[u], b, g);
+                for (int p = 0; p < 4; ++p) {
+                    const float2 ab0 = kab[(2 * p) * cgx], cd0 = kcd[(2 * p) * cgx];
+                    const float2 ab1 = kab[(2 * p + 1) * cgx], cd1 = kcd[(2 * p + 1) * cgx];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 ab = kab[i * cgx], cd = kcd[i * cgx];
-                        const float t = round_lowp(fmaf(v[i], ab.x, ab.y), b);
-                        const float du = act_bwd(g[i], t, act, b);
-                        acc[0][i] += du;
-                        acc[1][i] = fmaf(du, fmaf(v[i], cd.x, cd.y), acc[1][i]);
+                    for (int u = 0; u < U; ++u) {
+                        if (r + (h + u) * nrows < n_here) {
+                            const uint32_t yw[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+                            const uint32_t gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+                            const float2 yy = unpack2(yw[p], b), gg = unpack2(gw[p], b);
+                            const float t0 = round_lowp(fmaf(yy.x, ab0.x, ab0.y), b), t1 = round_lowp(fmaf(yy.y, ab1.x, ab1.y), b);
+                            const float du0 = act_bwd(gg.x, t0, ACT, b), du1 = act_bwd(gg.y, t1, ACT, b);
+                            acc[0][2 * p] += du0;
+                            acc[0][2 * p + 1] += du1;
+                            acc[1][2 * p] = fmaf(du0, fmaf(yy.x, cd0.x, cd0.y), acc[1][2 * p]);
+                            acc[1][2 * p + 1] = fmaf(du1, fmaf(yy.y, cd1.x, cd1.y), acc[1][2 * p + 1]);
+                            duw[u][p] = pack2(du0, du1, b);
+                        }
+                    }
+                }
+                // du is already a value of the activation dtype (act_bwd rounds it): the apply pass reads it back instead of
+                // re-deriving it from y and dz (exp + reciprocal + ~15 more instructions per element, which bound that pass)
+                if (ob) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int rr = r + (h + u) * nrows;
+                        if (rr < n_here)
+                            *reinterpret_cast<uint4*>(ob + static_cast<uint32_t>(rr) * static_cast<uint32_t>(du_pitch)) =
+                                make_uint4(duw[u][0], duw[u][1], duw[u][2], duw[u][3]);
                     }
                 }
             }
@@ -324,23 +353,27 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_reduce_kernel(const
     block_publish<2>(acc, cgx, nrows, channels, dst);
 }
 
-__global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const void* __restrict__ y, int y_pitch, const void* __restrict__ dz,
-                                                                          int dz_pitch, void* __restrict__ dy, int dy_pitch, long long rows,
-                                                                          int channels, int bf16, int act, int cgx, int rpb,
-                                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(kRedThreads, 4) bn_act_bwd_apply_kernel(const void* __restrict__ y, int y_pitch, const void* du, int du_pitch,
+                                                                          void* dy, int dy_pitch, long long rows, int channels, int bf16,
+                                                                          int cgx, int rpb, const float* __restrict__ mean,
+                                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                           const double* __restrict__ ws, float* __restrict__ dgamma,
                                                                           float* __restrict__ dbeta) {
+    // dy = du*a + y*c1 + c0 (see the table above).  du = dz * act'(t) comes from the reduce pass (stored in the dy buffer itself
+    // for SiLU layers -- each thread reads its 16 bytes before it overwrites them -- or is dz for linear layers): no
+    // transcendental work is left here, the pass is a pure 2-read 1-write stream.
     griddep_wait();  // PDL: the predecessor kernel has completed and flushed beyond this point
     griddep_launch_dependents();
-    __shared__ ChanTables tab;
+    __shared__ float2 tab_ac[kRedThreads];  // {a, c1}
+    __shared__ float tab_d[kRedThreads];    // c0
     const int nrows = kRedThreads / cgx;
     const int tx = threadIdx.x % cgx, ty = threadIdx.x / cgx;
     const int cg = blockIdx.x * cgx + tx;
     const float inv_rows = 1.0f / static_cast<float>(rows);
     for (int i = threadIdx.x; i < cgx * 8; i += kRedThreads) {
         const int c = blockIdx.x * cgx * 8 + i;
-        float2 ab = make_float2(0.f, 0.f), cd = make_float2(0.f, 0.f);
+        float2 ac = make_float2(0.f, 0.f);
+        float d = 0.f;
         if (c < channels) {
             const float db = static_cast<float>(ws[c]), dg = static_cast<float>(ws[channels + c]);
             if (blockIdx.y == 0) {
@@ -348,19 +381,18 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
                 dgamma[c] = dg;
             }
             const float is = invstd[c], m2 = -mean[c] * is;
-            ab.x = is * gamma[c];
-            ab.y = beta[c] - mean[c] * ab.x;
-            cd.x = -is * (dg * inv_rows) * ab.x;
-            cd.y = -(db * inv_rows + m2 * (dg * inv_rows)) * ab.x;
+            ac.x = is * gamma[c];
+            ac.y = -is * (dg * inv_rows) * ac.x;
+            d = -(db * inv_rows + m2 * (dg * inv_rows)) * ac.x;
         }
-        tab.ab[chan_slot(i, cgx)] = ab;
-        tab.cd[chan_slot(i, cgx)] = cd;
+        tab_ac[chan_slot(i, cgx)] = ac;
+        tab_d[chan_slot(i, cgx)] = d;
     }
     __syncthreads();
     if (cg * 8 >= channels) return;
     const bool b = bf16 != 0;
-    const float2* kab = tab.ab + tx;
-    const float2* kcd = tab.cd + tx;
+    const float2* kac = tab_ac + tx;  // channel i of this thread: [i * cgx], conflict-free
+    const float* kd = tab_d + tx;
     const long long r0 = static_cast<long long>(blockIdx.y) * rpb;
     const long long r1 = min(rows, r0 + rpb);
     for (long long r = r0 + ty; r < r1; r += kUnroll * nrows) {
@@ -370,7 +402,7 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
             const long long rr = r + u * nrows;
             if (rr < r1) {
                 yv[u] = ld16(y, rr * y_pitch + cg * 8);
-                gv[u] = ld16(dz, rr * dz_pitch + cg * 8);
+                gv[u] = ld16(du, rr * du_pitch + cg * 8);
             }
         }
 #pragma unroll
@@ -382,10 +414,8 @@ __global__ void __launch_bounds__(kRedThreads, 3) bn_act_bwd_apply_kernel(const 
                 unpack8(gv[u], b, g);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float2 ab = kab[i * cgx], cd = kcd[i * cgx];
-                    const float t = round_lowp(fmaf(v[i], ab.x, ab.y), b);
-                    const float du = act_bwd(g[i], t, act, b);
-                    v[i] = fmaf(du, ab.x, fmaf(v[i], cd.x, cd.y));
+                    const float2 ac = kac[i * cgx];
+                    v[i] = fmaf(g[i], ac.x, fmaf(v[i], ac.y, kd[i * cgx]));
                 }
                 st16(dy, rr * dy_pitch + cg * 8, pack8(v, b));
             }
@@ -670,13 +700,28 @@ extern "C" Y5_API int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* 
     if (!mean || !invstd || !gamma || !beta || !dgamma || !dbeta || !workspace || rows <= 0)
         return set_error(Y5_E_INVALID, "bn_act_bwd: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const RowGeom g = row_geom(channels, rows, true), ga = row_geom(channels, rows, false, 3);
+    static const int red_u = env_int("Y5_BN_RED_U", 4);
+    const RowGeom g = row_geom(channels, rows, true, red_u == 2 ? 3 : 2), ga = row_geom(channels, rows, false, 4);
     const dim3 grid = row_grid(g, channels, rows);
     count_launch(2);
-    launch_pdl(bn_act_bwd_reduce_kernel, grid, dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, rows, channels, dtype == Y5_BF16, act, g.cgx, g.rpb, mean, invstd,
-                                                           gamma, beta, static_cast<double*>(workspace));
-    launch_pdl(bn_act_bwd_apply_kernel, row_grid(ga, channels, rows), dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, act, ga.cgx, ga.rpb,
-                                                          mean, invstd, gamma, beta, static_cast<const double*>(workspace), dgamma, dbeta);
+    // SiLU layers: the reduce pass leaves du = dz * silu'(t) in the dy buffer and the apply pass finishes it in place; linear
+    // layers have du == dz
+    {
+        using RedFn = void (*)(const void*, int, const void*, int, long long, int, int, int, const float*, const float*, const float*, const float*,
+                               double*, void*, int);
+        static const RedFn table[2][2][2] = {
+            {{bn_act_bwd_reduce_kernel<4, false, false>, bn_act_bwd_reduce_kernel<4, false, true>},
+             {bn_act_bwd_reduce_kernel<4, true, false>, bn_act_bwd_reduce_kernel<4, true, true>}},
+            {{bn_act_bwd_reduce_kernel<2, false, false>, bn_act_bwd_reduce_kernel<2, false, true>},
+             {bn_act_bwd_reduce_kernel<2, true, false>, bn_act_bwd_reduce_kernel<2, true, true>}}};
+        // SiLU layers: the reduce pass leaves du = dz * silu'(t) in the dy buffer and the apply pass finishes it in place; linear
+        // layers have du == dz
+        launch_pdl(table[red_u == 2 ? 1 : 0][dtype == Y5_BF16 ? 1 : 0][act ? 1 : 0], grid, dim3(kRedThreads), 0, st, y, y_pitch, dz, dz_pitch, rows,
+                   channels, g.cgx, g.rpb, mean, invstd, gamma, beta, static_cast<double*>(workspace), act ? dy : static_cast<void*>(nullptr), dy_pitch);
+    }
+    launch_pdl(bn_act_bwd_apply_kernel, row_grid(ga, channels, rows), dim3(kRedThreads), 0, st, y, y_pitch, act ? static_cast<const void*>(dy) : dz,
+               act ? dy_pitch : dz_pitch, dy, dy_pitch, rows, channels, dtype == Y5_BF16, ga.cgx, ga.rpb, mean, invstd, gamma,
+               static_cast<const double*>(workspace), dgamma, dbeta);
     return launch_status("bn_act_bwd");
 }
 
