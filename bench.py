@@ -628,7 +628,7 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
 
     rec = None
     graphed = tc_ref = None
-    graph_dp = world > 1 and os.environ.get("Y5_BENCH_GRAPH_DP", "1") != "0"
+    graph_dp = world > 1 and os.environ.get("Y5_BENCH_GRAPH_DP", "0") != "0"
     if (world == 1 and rank == 0 and extras) or graph_dp:
         # whole step replayed from one CUDA graph through the public helper: what the kernels cost without Python.  N > 1: every
         # rank captures its step including the ONE all-reduce of the gradient arena (FusedSGD.data_parallel) and replays in lock-step.

@@ -75,5 +75,34 @@ def metrics(src, dst, workload):
     print(open(dst).read()[-600:])
 
 
+def launches_bw(src, dst, title="training step"):
+    """launch list with DRAM bytes: per kernel launches / time / share and the DRAM bandwidth it ran at (cold caches under ncu)."""
+    rows = read(src)
+    per = collections.OrderedDict()
+    for r in rows:
+        per.setdefault(r["ID"], {"name": short(r["Kernel Name"])})[r["Metric Name"]] = (r["Metric Value"], r["Metric Unit"])
+    agg = collections.OrderedDict()
+    for m in per.values():
+        g = lambda k: m.get(k, ("0", ""))  # noqa: E731
+        a = agg.setdefault(m["name"], [0, 0.0, 0.0, 0.0, 0.0])
+        us = to_us(*g("gpu__time_duration.sum"))
+        a[0] += 1
+        a[1] += us
+        a[2] += to_bytes(*g("dram__bytes_read.sum"))
+        a[3] += to_bytes(*g("dram__bytes_write.sum"))
+        a[4] = max(a[4], us)
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list of one {title} ({os.path.basename(src)}): gpu__time_duration.sum + dram bytes, --clock-control none\n\n")
+        f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+        f.write("| kernel | launches | total us | share | avg us | max us | DRAM read MB | DRAM write MB | DRAM GB/s |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0]:.1f} | {a[4]:.1f} | {a[2] / 1e6:.1f} | {a[3] / 1e6:.1f} | "
+                    f"{(a[2] + a[3]) / a[1] / 1e3:.0f} |\n")
+        f.write(f"\ntotal {tot:.1f} us over {sum(a[0] for a in agg.values())} launches, DRAM traffic "
+                f"{sum(a[2] + a[3] for a in agg.values()) / 1e9:.2f} GB\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "metrics": metrics}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "metrics": metrics, "launches_bw": launches_bw}[sys.argv[1]](*sys.argv[2:])

@@ -405,6 +405,61 @@ def _bn_ws(c: int, device) -> torch.Tensor:
     return _arena.take(2 * c, device)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Weight gradients off the critical path.  Per layer the backward is  bn_bwd -> {dgrad, wgrad}; only dgrad feeds the next
+# layer.  With `set_async_wgrad(True)` the weight-gradient kernels (and the KRSC -> OIHW copy behind them) are issued on a side
+# stream that waits for the layer's dy; the calling stream joins it once, in a callback the autograd engine runs at the end of
+# the backward pass (on the caller's stream).  Inside a captured CUDA graph that is a fork per layer and one join: the ~80
+# small, latency-bound wgrad launches fill SMs the main chain leaves idle instead of extending it.  Off by default because
+# anything that READS parameter gradients while backward is still running (DistributedDataParallel's bucket hooks, user
+# hooks) would race with the side stream; GraphedTrainStep -- which takes plain modules only -- turns it on.
+# ---------------------------------------------------------------------------------------------------------------------
+_async_wgrad = False
+_side_streams: dict = {}
+_pending: list = []  # operands of in-flight side-stream work: freed only after the join, so the allocator cannot recycle them early
+_join_armed = False
+
+
+def set_async_wgrad(on: bool) -> bool:
+    global _async_wgrad
+    old, _async_wgrad = _async_wgrad, bool(on)
+    return old
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = _side_streams[dev.index] = torch.cuda.Stream(dev)
+    return s
+
+
+def _join_side(dev) -> None:
+    global _join_armed
+    torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+    _pending.clear()
+    _join_armed = False
+
+
+def finish_async(dev) -> None:
+    """join the side stream if a backward pass left it un-joined (it raised before the engine ran the callback)"""
+    if _join_armed:
+        _join_side(dev)
+
+
+def _wgrad_async(dev, fn, keep):
+    """run fn() (wgrad launches) on the side stream after everything queued so far; arm the end-of-backward join"""
+    global _join_armed
+    side = _side_stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        out = fn()
+    _pending.append((keep, out))
+    if not _join_armed:
+        _join_armed = True
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _join_side(dev))
+    return out
+
+
 class _ConvBnAct(torch.autograd.Function):
     """z = act(BN(conv(x, w)))  with batch statistics (training) or running statistics (eval inside a training graph)."""
 
@@ -497,17 +552,22 @@ class _ConvBnAct(torch.autograd.Function):
         _lib.check(lib.y5_bn_act_bwd(y.data_ptr(), c, dz.data_ptr(), dzp, dy.data_ptr(), c, rows, c, code, mean.data_ptr(), invstd.data_ptr(),
                                      g32.data_ptr(), b32.data_ptr(), 1 if act else 0, dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
                                      _st(dev)), "bn_act_bwd")
-        dw = stem_wgrad_wide(x, dy) if ctx.wide else conv_wgrad(x, dy, ke, se, pe)
-        if stem:  # (O,16,3,3) gradient of the space-to-depth filter -> (O,3,6,6)
-            _, inv_idx = _stem_index(dev)
-            dw = dw.reshape(dw.shape[0], -1)[:, inv_idx].view(weight.shape)
+        def wgrad():
+            g = stem_wgrad_wide(x, dy) if ctx.wide else conv_wgrad(x, dy, ke, se, pe)
+            if stem:  # (O,16,3,3) gradient of the space-to-depth filter -> (O,3,6,6)
+                _, inv_idx = _stem_index(dev)
+                g = g.reshape(g.shape[0], -1)[:, inv_idx].view(weight.shape)
+            return g.to(weight.dtype)
+
+        # (an existing .grad would be accumulated into by autograd on the calling stream right after this function returns)
+        dw = _wgrad_async(dev, wgrad, (x, dy)) if (_async_wgrad and weight.grad is None) else wgrad()
         dx = None
         if ctx.needs_input_grad[0]:
             if stem:
                 raise NotImplementedError("y5b200: gradient w.r.t. the input image")
             dx = conv_dgrad(dy, None, k, s, p, (x.shape[2], x.shape[3]), wp_dgrad=wp_dg, cin=x.shape[1], block_k=ctx.bk_d)
         dres = dz_in if ctx.needs_input_grad[6] else None  # z = residual + act(bn(y)): the shortcut's gradient is dz itself
-        return (dx, dw.to(weight.dtype), dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, dres, None, None, None, None, None,
+        return (dx, dw, dgamma.to(ctx.pdtypes[0]), dbeta.to(ctx.pdtypes[1]), None, None, dres, None, None, None, None, None,
                 None, None, None)
 
 

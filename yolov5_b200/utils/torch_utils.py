@@ -395,13 +395,21 @@ class GraphedTrainStep:
                             "all-reduce is capturable")
         world = optimizer._dp[1] if optimizer._dp is not None else 1
 
+        from .. import train_ops
+
         def step():
             with torch.autocast("cuda", dtype=amp_dtype):
                 pred = model(self.img)
             loss, items = compute_loss(pred, self.tgt)
             if world > 1:
                 loss = loss * world  # train.py:405: the all-reduce averages over ranks, the reference rescales
-            scaler.scale(loss).backward()
+            # weight gradients on a side stream, joined at the end of backward: a fork per layer in the captured graph
+            prev = train_ops.set_async_wgrad(os.environ.get("Y5_ASYNC_WGRAD", "0") != "0")
+            try:
+                scaler.scale(loss).backward()
+            finally:
+                train_ops.set_async_wgrad(prev)
+                train_ops.finish_async(dev)
             optimizer.fused_step(scaler=scaler, max_norm=max_norm, ema=ema, model=model)
             optimizer.zero_grad(set_to_none=True)  # gradients return to the graph's private pool: same addresses at every replay
             self.items.copy_(items)
@@ -429,8 +437,6 @@ class GraphedTrainStep:
             step()
         # the capture baked in the address of the BN-sum arena (allocated during warm-up, outside the graph's pool): keep it
         # alive even if a later eager forward of another shape makes the arena grow
-        from .. import train_ops
-
         self._arena_buf = train_ops._arena.buf
         self._pack_plans = list(model.__dict__.get("_y5_pack_plans", {}).values())  # persistent packed-weight buffers + tables
         # undo what warm-up and capture touched: weights are unchanged (lr 0 / capture does not execute), BN running statistics
