@@ -453,7 +453,12 @@ def _wgrad_async(dev, fn, keep):
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         out = fn()
-    _pending.append((keep, out))
+    # only the OPERANDS are parked: an extra reference to the gradient itself would make autograd's AccumulateGrad clone it
+    # instead of adopting it -- a copy kernel on the calling stream, reading the gradient before the side stream has written it
+    # (measured: exactly that race, the graph-captured step walked the weights differently from the eager one)
+    _pending.append(keep)
+    if os.environ.get("Y5_ASYNC_WGRAD_JOIN_NOW"):  # diagnostic: same streams, no concurrency
+        torch.cuda.current_stream(dev).wait_stream(side)
     if not _join_armed:
         _join_armed = True
         torch.autograd.Variable._execution_engine.queue_callback(lambda: _join_side(dev))

@@ -404,7 +404,7 @@ class GraphedTrainStep:
             if world > 1:
                 loss = loss * world  # train.py:405: the all-reduce averages over ranks, the reference rescales
             # weight gradients on a side stream, joined at the end of backward: a fork per layer in the captured graph
-            prev = train_ops.set_async_wgrad(os.environ.get("Y5_ASYNC_WGRAD", "0") != "0")
+            prev = train_ops.set_async_wgrad(os.environ.get("Y5_ASYNC_WGRAD", "1") != "0")
             try:
                 scaler.scale(loss).backward()
             finally:
