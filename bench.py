@@ -712,6 +712,9 @@ def train_leg(D: Dist, model_name, bs, size, dt, steps, warmup, extras=True):
             roof = {"kernel": "whole training step (conv_gemm fwd+dgrad, conv_wgrad, BN/SiLU passes, fused optimizer)", "bound": "hbm", "achieved": gbs,
                     "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                     "algorithmic_bytes_per_step": prog_bytes, "flops_per_step": flops, "tensor_tflops": flops / (ms_step / 1e3) / 1e12}
+            if isinstance(graphed, dict) and graphed.get("ms_per_step"):  # the same step without Python between the launches
+                g_gbs = prog_bytes / (graphed["ms_per_step"] / 1e3) / 1e9
+                roof["graph_replayed"] = {"achieved": g_gbs, "frac": g_gbs / pk["hbm"], "tensor_tflops": flops / (graphed["ms_per_step"] / 1e3) / 1e12}
             del em, prog
         except Exception:  # noqa: BLE001
             pass
