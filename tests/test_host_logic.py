@@ -92,8 +92,12 @@ def test_module_pickles_without_engine_state():
 
     m = DetectionModel("yolov5n")
     m.__dict__["_y5_programs"] = {"x": object()}
+    m.__dict__["_y5_pack_plans"] = {("cpu", torch.float16): object()}
     m2 = pickle.loads(pickle.dumps(m))
-    assert "_y5_programs" not in m2.__dict__
+    assert "_y5_programs" not in m2.__dict__ and "_y5_pack_plans" not in m2.__dict__
+    import copy
+
+    assert "_y5_pack_plans" not in copy.deepcopy(m).__dict__  # ModelEMA's deepcopy starts without the training-path buffers
     assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
 
 
@@ -166,3 +170,59 @@ def test_training_forward_rejects_cpu_and_fp32():
     m = DetectionModel("yolov5n").train()
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 64, 64))
+
+
+def test_pack_plan_host_logic(monkeypatch):
+    """train_ops.PackPlan without a GPU: registration marks the table dirty, begin() builds one y5_pack_item per registered filter
+    (pointers, shapes, pads), covers every element of [fwd | dgrad] with chunk entries exactly once, bumps the epoch, and lookup()
+    only hands out buffers packed in the CURRENT forward with the same geometry."""
+    import contextlib
+    import ctypes
+
+    from yolov5_b200 import _lib, train_ops
+
+    calls = []
+
+    class Fake:
+        def y5_weight_pack_chunk_elems(self):
+            return 1000
+
+        def y5_weight_pack_multi(self, items, ci, cx, n, dtype, stream):
+            calls.append((items, ci, cx, n, dtype))
+            return 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: Fake())
+    monkeypatch.setattr(_lib, "on", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(train_ops, "_st", lambda dev: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    dev = torch.device("cpu")
+    plan = train_ops.PackPlan(dev, torch.float16)
+    w1 = torch.nn.Parameter(torch.randn(24, 16, 3, 3))
+    w2 = torch.nn.Parameter(torch.randn(8, 24, 1, 1))
+    f1, d1 = torch.empty(24, 3, 3, 64, dtype=torch.float16), torch.empty(16, 3, 3, 64, dtype=torch.float16)
+    f2 = torch.empty(8, 1, 1, 64, dtype=torch.float16)
+    plan.begin()  # nothing registered: no launch
+    assert not calls and plan.lookup(w1, 64, 64, True) is None
+    plan.register(w1, f1, d1, 64, 64, 64, 64)
+    plan.register(w2, f2, None, 64, 0, 64, 0)
+    assert plan.dirty and plan.lookup(w1, 64, 64, True) is None  # registered during this forward: packed by the layer itself
+    plan.begin()
+    assert len(calls) == 1 and not plan.dirty
+    items, ci, cx, n, ents = plan.table
+    arr = (_lib.PackItem * 2).from_buffer_copy(items.numpy().tobytes())
+    assert (arr[0].w, arr[0].fwd, arr[0].dgrad) == (w1.data_ptr(), f1.data_ptr(), d1.data_ptr())
+    assert (arr[0].out_c, arr[0].in_c, arr[0].ksize, arr[0].in_c_pad, arr[0].out_c_pad) == (24, 16, 3, 64, 64)
+    assert (arr[1].w, arr[1].fwd, arr[1].dgrad) == (w2.data_ptr(), f2.data_ptr(), None) and arr[1].w_dtype == _lib.Y5_F32
+    total = [24 * 9 * 64 + 16 * 9 * 64, 8 * 64]
+    per_item = [[int(x) for t, x in zip(ci.tolist(), cx.tolist()) if t == i] for i in range(2)]
+    for i in range(2):
+        assert per_item[i] == list(range((total[i] + 999) // 1000))  # chunks 0..ceil(total/1000)-1, each once
+    assert n == sum(len(v) for v in per_item) == calls[0][3]
+    assert plan.lookup(w1, 64, 64, True) == (f1, d1) and plan.lookup(w2, 64, 0, False) == (f2, None)
+    assert plan.lookup(w2, 64, 64, True) is None      # a data gradient is wanted but was never packed
+    assert plan.lookup(w1, 16, 64, True) is None      # another K-block geometry
+    w1.data = torch.randn(24, 16, 3, 3)               # storage replaced (e.g. .to()): stale pointer must not be used
+    assert plan.lookup(w1, 64, 64, True) is None
+    plan.begin()
+    assert len(plan.table[4]) == 1                    # the stale entry left the table, w2 stays
+    assert ctypes.sizeof(_lib.PackItem) == 48

@@ -47,6 +47,7 @@ class _EngineLayer(nn.Module):
         d = self.__dict__.copy()
         d.pop("_y5_programs", None)
         d.pop("_y5_tensors", None)
+        d.pop("_y5_pack_plans", None)  # persistent packed-weight buffers of the training path (train_ops.PackPlan)
         return d
 
     def _apply(self, fn, *a, **k):

@@ -132,6 +132,11 @@ class PackPlan:
     def begin(self):
         """Start of a training forward: one launch packs every registered filter from the current master weights."""
         self.epoch += 1
+        if not self.dirty and self.table is not None:
+            for e in self.table[4]:  # a parameter whose storage was replaced (.to(), .data = ...): its table row points at the old one
+                if e.wptr != e.weight.data_ptr():
+                    self.dirty = True
+                    break
         if self.dirty or self.table is None:
             if torch.cuda.is_current_stream_capturing():
                 return  # no host-to-device table upload inside a capture: this forward packs layer by layer
