@@ -261,7 +261,9 @@ int y5_bn_act_fwd(const void* y, int32_t y_pitch, void* z, int32_t z_pitch, int6
                   int32_t dtype, float* mean, float* invstd, const float* gamma, const float* beta, int32_t act,
                   const void* sums, float eps, float momentum, float* running_mean, float* running_var,
                   const void* residual, int32_t res_pitch, void* stream);
-/* given dz: dy (gradient w.r.t. the conv output), dgamma, dbeta (fp32, overwritten) */
+/* given dz: dy (gradient w.r.t. the conv output), dgamma, dbeta (fp32, overwritten).  Two launches: the reduce pass forms
+ * du = dz * act'(bn(y)) and its two column sums and, for Y5_ACT_SILU, parks du in the dy buffer; the apply pass turns it into dy
+ * in place.  dy may alias dz (every element is read before it is written) but not y. */
 int y5_bn_act_bwd(const void* y, int32_t y_pitch, const void* dz, int32_t dz_pitch, void* dy, int32_t dy_pitch,
                   int64_t rows, int32_t channels, int32_t dtype, const float* mean, const float* invstd,
                   const float* gamma, const float* beta, int32_t act, float* dgamma, float* dbeta, void* workspace,
