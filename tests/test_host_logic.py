@@ -226,3 +226,32 @@ def test_pack_plan_host_logic(monkeypatch):
     plan.begin()
     assert len(plan.table[4]) == 1                    # the stale entry left the table, w2 stays
     assert ctypes.sizeof(_lib.PackItem) == 48
+
+
+def test_bn_backward_algebra_of_the_kernels_matches_autograd():
+    """The two-pass form the CUDA kernels use for the backward of z = SiLU(BN_batchstats(y)) (train_kernels.cu: the reduce pass
+    forms du = dz * silu'(t) and its column sums, the apply pass dy = du*a + y*c1 + c0 from four per-channel constants),
+    restated in float64 and compared with torch autograd of the reference expression (models/common.py:86-88)."""
+    torch.manual_seed(7)
+    rows, c, eps = 257, 24, 1e-3
+    y = torch.randn(rows, c, dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(c, dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(c, dtype=torch.float64, requires_grad=True)
+    dz = torch.randn(rows, c, dtype=torch.float64)
+    z = F.silu(F.batch_norm(y, None, None, gamma, beta, training=True, eps=eps))
+    z.backward(dz)
+    with torch.no_grad():
+        mean, var = y.mean(0), y.var(0, unbiased=False)
+        invstd = (var + eps).rsqrt()
+        a = invstd * gamma                      # constants of the kernels' tables
+        b = beta - mean * a
+        t = y * a + b                           # BN output
+        sg = torch.sigmoid(t)
+        du = dz * sg * (1 + t * (1 - sg))       # reduce pass: du, sum du, sum du * xhat
+        xhat = y * invstd - mean * invstd
+        dbeta, dgamma = du.sum(0), (du * xhat).sum(0)
+        c1 = -invstd * (dgamma / rows) * a      # apply pass
+        c0 = -(dbeta / rows + (-mean * invstd) * (dgamma / rows)) * a
+        dy = du * a + y * c1 + c0
+    assert torch.allclose(dy, y.grad, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(dgamma, gamma.grad, rtol=1e-10, atol=1e-12) and torch.allclose(dbeta, beta.grad, rtol=1e-10, atol=1e-12)
